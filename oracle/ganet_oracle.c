@@ -1,0 +1,494 @@
+/*
+ * ganet_oracle.c -- CPU restatement of GANet's guided-aggregation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing on the product path may link, import or
+ * call this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and there only as the checker.
+ *
+ * Every function restates one piece of the reference (paths relative to the
+ * reference tree, libs/GANet/src/GANet_kernel.cu unless stated otherwise):
+ *
+ *   oracle_sga_forward    sga_{down,up,right,left}_forward (:66-127, :285-346,
+ *                         :507-565, :720-778) + Max (:23-36) in the launch
+ *                         order of sga_kernel_forward (:958-994)
+ *   oracle_sga_backward   get_temp_grad (:38-48), MaxDepth (:50-64),
+ *                         sga_*_data_backward (:129-208, :348-426, :567-640,
+ *                         :780-854), sga_*_weight_backward (:210-281, :428-505,
+ *                         :642-718, :856-933) in the order of
+ *                         sga_kernel_backward (:1041-1128: left, down, up, right)
+ *   oracle_lga_forward    lga_filtering_forward (:1131-1175)
+ *   oracle_lga_backward   lga_filter_backward (:1177-1216) then
+ *                         lga_data_backward (:1218-1269), as lga_backward (:1299-1322)
+ *   oracle_lga2_*         Lga2Function (libs/GANet/functions/GANet.py:174-203)
+ *   oracle_cost_volume_*  GetCostVolume.forward (libs/GANet/modules/GANet.py:119-134)
+ *   oracle_disp_regr_*    DisparityRegression.forward (modules/GANet.py:142-148)
+ *
+ * The four scan directions are written ONCE in canonical form (scan index t,
+ * lane index l) instead of four hand-unrolled copies as upstream; the geometry
+ * table below maps (dir, t, l) -> (h, w).
+ *
+ * Rounding.  All arithmetic is fp32.  `fused == 0` evaluates every `a += b*c`
+ * as a separate multiply and add (what g++ produces for the reference kernel
+ * bodies compiled for the host: oracle/_ref/libganet_ref_cpu.so).  `fused == 1`
+ * reproduces the FMA contraction nvcc 12.9 applies to the reference's forward
+ * scans on sm_100a (read from the SASS of the unmodified reference build,
+ * SURVEY.md section 7-H1):
+ *     first scan step : five chained fma(x, w_k, acc), acc starting at +0
+ *     later steps, even d : fma, fma, mul+add, mul+add, fma
+ *     later steps, odd  d : fma, fma, fma,     mul+add, fma
+ * which is what makes the direction mask and the depth arg-max bit-exact
+ * against the reference CUDA kernels.  Backward sums are compared with a
+ * tolerance, so `fused` only selects the forward recompute there.
+ *
+ * Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
+ * section 8c).  This file is pinned instead against the reference's own
+ * kernel bodies compiled for the host (tests/test_oracle_vs_ref.py, bit-exact
+ * with fused=0), against vectors generated from them and committed under
+ * tests/golden/, and on the GPU box against the unmodified reference CUDA
+ * extension (oracle/_ref/GANet*.so, bit-exact with fused=1).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define API __attribute__((visibility("default")))
+
+/* ---- scan geometry ------------------------------------------------------ */
+/* dir 0 down : t = h,       lane = w      dir 1 up   : t = H-1-h, lane = w
+ * dir 2 right: t = w,       lane = h      dir 3 left : t = W-1-w, lane = h
+ * (kernel headers :66, :285, :507, :720; index math :77-78, :298-299, :520-521) */
+static inline int scan_len(int dir, int H, int W) { return dir < 2 ? H : W; }
+static inline int lane_cnt(int dir, int H, int W) { return dir < 2 ? W : H; }
+static inline int64_t pix(int dir, int t, int l, int H, int W)
+{
+    switch (dir) {
+    case 0: return (int64_t)t * W + l;
+    case 1: return (int64_t)(H - 1 - t) * W + l;
+    case 2: return (int64_t)l * W + t;
+    default: return (int64_t)l * W + (W - 1 - t);
+    }
+}
+
+/* one a += b*c in the two rounding flavours */
+static inline float mac_sep(float acc, float a, float b) { float m = a * b; return acc + m; }
+static inline float mac_fma(float acc, float a, float b) { return fmaf(a, b, acc); }
+
+/*
+ * One directional aggregation of one (n,c) slice, Appendix A.1 of SURVEY.md.
+ * x, A: [D][H*W]; g: [5][H*W].  A must not alias x.
+ * idx (optional, [H*W]) receives the first arg-max over d of A at every pixel
+ * (what MaxDepth :50-64 computes from the finished volume).
+ */
+static void scan_forward(const float *x, const float *g, float *A, int32_t *idx,
+                         int dir, int D, int H, int W, int fused)
+{
+    const int64_t HW = (int64_t)H * W;
+    const int T = scan_len(dir, H, W), L = lane_cnt(dir, H, W);
+    for (int l = 0; l < L; l++) {
+        int kp = 0;
+        for (int t = 0; t < T; t++) {
+            const int64_t p = pix(dir, t, l, H, W);
+            const int64_t q = t > 0 ? pix(dir, t - 1, l, H, W) : 0;
+            const float w0 = g[p], w1 = g[HW + p], w2 = g[2 * HW + p],
+                        w3 = g[3 * HW + p], w4 = g[4 * HW + p];
+            const int k = kp;   /* arg-max of the previous position (:87, :122-123) */
+            kp = 0;
+            for (int d = 0; d < D; d++) {
+                const float xv = x[d * HW + p];
+                float acc = 0.0f;
+                if (t == 0) {
+                    /* all five terms use the raw input (:99-119 else-branches) */
+                    if (fused) {
+                        acc = mac_fma(acc, xv, w0); acc = mac_fma(acc, xv, w1);
+                        acc = mac_fma(acc, xv, w2); acc = mac_fma(acc, xv, w3);
+                        acc = mac_fma(acc, xv, w4);
+                    } else {
+                        acc = mac_sep(acc, xv, w0); acc = mac_sep(acc, xv, w1);
+                        acc = mac_sep(acc, xv, w2); acc = mac_sep(acc, xv, w3);
+                        acc = mac_sep(acc, xv, w4);
+                    }
+                } else {
+                    const float pc = A[d * HW + q];
+                    const float pm = d >= 1 ? A[(d - 1) * HW + q] : xv;      /* :105-109 */
+                    const float pp = d + 1 < D ? A[(d + 1) * HW + q] : xv;   /* :110-114 */
+                    const float pk = A[k * HW + q];                          /* :115-117 */
+                    if (fused) {
+                        acc = mac_fma(acc, xv, w0);
+                        acc = mac_fma(acc, pc, w1);
+                        acc = (d & 1) ? mac_fma(acc, pm, w2) : mac_sep(acc, pm, w2);
+                        acc = mac_sep(acc, pp, w3);
+                        acc = mac_fma(acc, pk, w4);
+                    } else {
+                        acc = mac_sep(acc, xv, w0); acc = mac_sep(acc, pc, w1);
+                        acc = mac_sep(acc, pm, w2); acc = mac_sep(acc, pp, w3);
+                        acc = mac_sep(acc, pk, w4);
+                    }
+                }
+                A[d * HW + p] = acc;
+                if (A[kp * HW + p] < acc) kp = d;    /* strict <: first maximum wins (:122) */
+            }
+            if (idx) idx[p] = kp;
+        }
+    }
+}
+
+/* ---- SGA forward --------------------------------------------------------- */
+/*
+ * x, out: (N,C,D,H,W); g0..g3: (N,C,5,H,W); mask: (N,C,D,H,W) uint8 direction id.
+ * dir_out (optional): 4 volumes (dir, N,C,D,H,W) with every directional aggregate.
+ */
+API int oracle_sga_forward(const float *x, const float *g0, const float *g1,
+                           const float *g2, const float *g3, float *out,
+                           uint8_t *mask, float *dir_out,
+                           int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int fused)
+{
+    const int64_t HW = H * W, S = D * HW, NC = N * C;
+    const float *g[4] = { g0, g1, g2, g3 };
+    int fail = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t s = 0; s < NC; s++) {
+        float *A = (float *)malloc(sizeof(float) * S);
+        if (!A) { fail = 1; continue; }
+        float *o = out + s * S;
+        uint8_t *m = mask + s * S;
+        for (int dir = 0; dir < 4; dir++) {
+            scan_forward(x + s * S, g[dir] + s * 5 * HW, A, NULL, dir, (int)D, (int)H, (int)W, fused);
+            if (dir_out) memcpy(dir_out + (dir * NC + s) * S, A, sizeof(float) * S);
+            if (dir == 0) {                       /* :962-968: out = down, mask = 0 */
+                memcpy(o, A, sizeof(float) * S);
+                memset(m, 0, S);
+            } else {                              /* Max :23-36 */
+                for (int64_t i = 0; i < S; i++)
+                    if (o[i] < A[i]) { o[i] = A[i]; m[i] = (uint8_t)dir; }
+            }
+        }
+        free(A);
+    }
+    return fail;
+}
+
+/* ---- SGA backward -------------------------------------------------------- */
+/*
+ * One direction of one slice: data backward (A.3) then weight backward.
+ * Tg: [D][HW] holds gradOut*[mask==dir] on entry, the propagated T on exit.
+ * gI accumulates (+=), gw ([5][HW]) accumulates (+=) like the reference.
+ */
+static void scan_backward(const float *x, const float *g, const float *A, const int32_t *idx,
+                          float *Tg, float *gI, float *gw, int dir, int D, int H, int W)
+{
+    const int64_t HW = (int64_t)H * W;
+    const int T = scan_len(dir, H, W), L = lane_cnt(dir, H, W);
+    for (int l = 0; l < L; l++) {
+        /* data backward, reverse scan order (:144-181) */
+        for (int t = T - 1; t >= 0; t--) {
+            const int64_t p = pix(dir, t, l, H, W);
+            const int has_next = t + 1 < T;
+            const int64_t r = has_next ? pix(dir, t + 1, l, H, W) : 0;
+            const float w0 = g[p];
+            for (int d = 0; d < D; d++) {
+                float temp = Tg[d * HW + p];
+                if (has_next) temp += Tg[d * HW + r] * g[HW + r];
+                if (has_next && d + 1 < D) temp += Tg[(d + 1) * HW + r] * g[2 * HW + r];
+                if (has_next && d - 1 >= 0) temp += Tg[(d - 1) * HW + r] * g[3 * HW + r];
+                Tg[d * HW + p] = temp;
+                gI[d * HW + p] += temp * w0;
+            }
+            if (has_next) {                                   /* max-path term (:167-178) */
+                const int k = idx[p];
+                float temp = 0.0f;
+                for (int d = 0; d < D; d++) temp += Tg[d * HW + r] * g[4 * HW + r];
+                Tg[k * HW + p] += temp;
+                gI[k * HW + p] += temp * w0;
+            }
+        }
+        for (int t = 0; t < T; t++) {                         /* depth-edge terms (:200-207) */
+            const int64_t p = pix(dir, t, l, H, W);
+            gI[p] += Tg[p] * g[2 * HW + p];
+            gI[(D - 1) * HW + p] += Tg[(D - 1) * HW + p] * g[3 * HW + p];
+        }
+        /* weight backward (:210-281), one pixel at a time */
+        for (int t = 0; t < T; t++) {
+            const int64_t p = pix(dir, t, l, H, W);
+            float a = gw[p];
+            for (int i = 0; i < D; i++) a += Tg[i * HW + p] * x[i * HW + p];
+            gw[p] = a;
+            if (t >= 1) {
+                const int64_t q = pix(dir, t - 1, l, H, W);
+                a = gw[HW + p];
+                for (int i = 0; i < D; i++) a += Tg[i * HW + p] * A[i * HW + q];
+                gw[HW + p] = a;
+
+                a = gw[2 * HW + p];
+                a += Tg[p] * x[p];
+                for (int i = 1; i < D; i++) a += Tg[i * HW + p] * A[(i - 1) * HW + q];
+                gw[2 * HW + p] = a;
+
+                a = gw[3 * HW + p];
+                a += Tg[(D - 1) * HW + p] * x[(D - 1) * HW + p];
+                for (int i = 0; i < D - 1; i++) a += Tg[i * HW + p] * A[(i + 1) * HW + q];
+                gw[3 * HW + p] = a;
+
+                const int k = idx[q];
+                a = gw[4 * HW + p];
+                for (int i = 0; i < D; i++) a += Tg[i * HW + p] * A[k * HW + q];
+                gw[4 * HW + p] = a;
+            }
+        }
+    }
+}
+
+/*
+ * gradIn: (N,C,D,H,W); gg0..gg3: (N,C,5,H,W); all overwritten (the reference
+ * accumulates into zero-filled buffers, functions/GANet.py:33-39).
+ * max_idx (optional, (N,C,H,W) int32): depth arg-max of the LAST processed
+ * direction (right), which is what the reference leaves in its max_idx buffer.
+ */
+API int oracle_sga_backward(const float *x, const float *g0, const float *g1,
+                            const float *g2, const float *g3, const uint8_t *mask,
+                            const float *gradOut, float *gradIn, float *gg0, float *gg1,
+                            float *gg2, float *gg3, int32_t *max_idx,
+                            int64_t N, int64_t C, int64_t D, int64_t H, int64_t W, int fused)
+{
+    const int64_t HW = H * W, S = D * HW, NC = N * C;
+    const float *g[4] = { g0, g1, g2, g3 };
+    float *gg[4] = { gg0, gg1, gg2, gg3 };
+    static const int order[4] = { 3, 0, 1, 2 };               /* :1040, :1061, :1084, :1106 */
+    int fail = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t s = 0; s < NC; s++) {
+        float *A = (float *)malloc(sizeof(float) * S);
+        float *Tg = (float *)malloc(sizeof(float) * S);
+        int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * HW);
+        if (!A || !Tg || !idx) { fail = 1; free(A); free(Tg); free(idx); continue; }
+        float *gi = gradIn + s * S;
+        memset(gi, 0, sizeof(float) * S);
+        for (int o = 0; o < 4; o++) {
+            const int dir = order[o];
+            float *gw = gg[dir] + s * 5 * HW;
+            memset(gw, 0, sizeof(float) * 5 * HW);
+            scan_forward(x + s * S, g[dir] + s * 5 * HW, A, idx, dir, (int)D, (int)H, (int)W, fused);
+            for (int64_t i = 0; i < S; i++)                   /* get_temp_grad :38-48 */
+                Tg[i] = mask[s * S + i] == dir ? gradOut[s * S + i] : 0.0f;
+            scan_backward(x + s * S, g[dir] + s * 5 * HW, A, idx, Tg, gi, gw, dir, (int)D, (int)H, (int)W);
+            if (max_idx && dir == 2) memcpy(max_idx + s * HW, idx, sizeof(int32_t) * HW);
+        }
+        free(A); free(Tg); free(idx);
+    }
+    return fail;
+}
+
+/* ---- LGA ----------------------------------------------------------------- */
+/*
+ * One LGA pass.  x, y: (B, D, H, W); f: (B, 3*(2R+1)^2, H, W) where B is the
+ * batch (4-D op, lga_forward :1271) or batch*channels (5-D op, lga3d_forward
+ * :1324).  y is overwritten (reference: += into a zeroed buffer).
+ */
+API int oracle_lga_forward(const float *x, const float *f, float *y,
+                           int64_t B, int64_t D, int64_t H, int64_t W, int R)
+{
+    const int64_t HW = H * W;
+    const int ws = 2 * R + 1, F = 3 * ws * ws;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        for (int64_t d = 0; d < D; d++)
+            for (int64_t h = 0; h < H; h++)
+                for (int64_t w = 0; w < W; w++) {
+                    const int64_t idx = ((b * D + d) * H + h) * W + w;
+                    const int64_t fb = b * F * HW + h * W + w;
+                    float acc = 0.0f;
+                    for (int dd = -1; dd <= 1; dd++)
+                        for (int r = -R; r <= R; r++)
+                            for (int c = -R; c <= R; c++) {
+                                const int64_t d2 = d + dd, h2 = h + r, w2 = w + c;
+                                int64_t shift = 0;          /* any axis out of range -> centre voxel (:1162-1165) */
+                                if (d2 >= 0 && h2 >= 0 && w2 >= 0 && d2 < D && h2 < H && w2 < W)
+                                    shift = dd * HW + r * W + c;
+                                const int loc = (dd + 1) * ws * ws + (r + R) * ws + (c + R);
+                                acc += x[idx + shift] * f[fb + loc * HW];
+                            }
+                    y[idx] = acc;
+                }
+    return 0;
+}
+
+/*
+ * One LGA backward pass.  gf ACCUMULATES (+=) like the reference (:1207);
+ * gx is overwritten (reference memsets it, :1316).  gx must not alias go.
+ */
+API int oracle_lga_backward(const float *x, const float *f, const float *go,
+                            float *gx, float *gf,
+                            int64_t B, int64_t D, int64_t H, int64_t W, int R)
+{
+    const int64_t HW = H * W;
+    const int ws = 2 * R + 1, F = 3 * ws * ws;
+    /* filter gradient (:1177-1216) */
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        for (int loc = 0; loc < F; loc++) {
+            const int dd = loc / (ws * ws) - 1;
+            const int r = (loc / ws) % ws - R;
+            const int c = loc % ws - R;
+            for (int64_t h = 0; h < H; h++)
+                for (int64_t w = 0; w < W; w++) {
+                    const int64_t base = b * D * HW + h * W + w;
+                    const int64_t h2 = h + r, w2 = w + c;
+                    float acc = gf[(b * F + loc) * HW + h * W + w];
+                    for (int64_t i = 0; i < D; i++) {
+                        const int64_t d2 = i + dd;
+                        if (h2 >= 0 && w2 >= 0 && d2 >= 0 && h2 < H && w2 < W && d2 < D)
+                            acc += go[base + i * HW] * x[base + i * HW + dd * HW + r * W + c];
+                        else
+                            acc += go[base + i * HW] * x[base + i * HW];
+                    }
+                    gf[(b * F + loc) * HW + h * W + w] = acc;
+                }
+        }
+    /* data gradient (:1218-1269) */
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        for (int64_t d = 0; d < D; d++)
+            for (int64_t h = 0; h < H; h++)
+                for (int64_t w = 0; w < W; w++) {
+                    const int64_t idx = ((b * D + d) * H + h) * W + w;
+                    const int64_t fb = b * F * HW + h * W + w;
+                    float acc = 0.0f;
+                    for (int dd = -1; dd <= 1; dd++)
+                        for (int r = -R; r <= R; r++)
+                            for (int c = -R; c <= R; c++) {
+                                const int64_t d2 = d + dd, h2 = h + r, w2 = w + c;
+                                if (d2 >= 0 && h2 >= 0 && w2 >= 0 && d2 < D && h2 < H && w2 < W) {
+                                    const int loc = (-dd + 1) * ws * ws + (-r + R) * ws + (-c + R);
+                                    acc += go[idx + dd * HW + r * W + c] * f[fb + r * W + c + loc * HW];
+                                } else {
+                                    const int loc = (dd + 1) * ws * ws + (r + R) * ws + (c + R);
+                                    acc += go[idx] * f[fb + loc * HW];
+                                }
+                            }
+                    gx[idx] = acc;
+                }
+    return 0;
+}
+
+/* `passes` successive LGA passes with the same filters (Lga2Function.forward,
+ * functions/GANet.py:176-187 for passes == 2; Lga3Function :143-157 for 3).
+ * tmp: (passes-1) volumes of scratch that receive the intermediates y1, y2... */
+API int oracle_lga_multi_forward(const float *x, const float *f, float *y, float *tmp,
+                                 int64_t B, int64_t D, int64_t H, int64_t W, int R, int passes)
+{
+    const int64_t V = B * D * H * W;
+    const float *src = x;
+    for (int p = 0; p < passes; p++) {
+        float *dst = (p == passes - 1) ? y : tmp + (int64_t)p * V;
+        oracle_lga_forward(src, f, dst, B, D, H, W, R);
+        src = dst;
+    }
+    return 0;
+}
+
+/* Backward of the above (functions/GANet.py:189-203).  tmp holds the
+ * intermediates written by the forward; scratch: 2 volumes.  gx, gf overwritten. */
+API int oracle_lga_multi_backward(const float *x, const float *f, const float *tmp,
+                                  const float *go, float *gx, float *gf, float *scratch,
+                                  int64_t B, int64_t D, int64_t H, int64_t W, int R, int passes)
+{
+    const int64_t V = B * D * H * W;
+    const int ws = 2 * R + 1, F = 3 * ws * ws;
+    memset(gf, 0, sizeof(float) * B * F * H * W);
+    float *cur = scratch, *nxt = scratch + V;
+    memcpy(cur, go, sizeof(float) * V);
+    for (int p = passes - 1; p >= 0; p--) {
+        const float *inp = (p == 0) ? x : tmp + (int64_t)(p - 1) * V;
+        float *dst = (p == 0) ? gx : nxt;
+        oracle_lga_backward(inp, f, cur, dst, gf, B, D, H, W, R);
+        float *sw = cur; cur = nxt; nxt = sw;
+    }
+    return 0;
+}
+
+/* ---- GetCostVolume (modules/GANet.py:119-134) ------------------------------ */
+/* x, y: (N,C,H,W) -> cost: (N,2C,Dm,H,W), Dm = maxdisp+1 */
+API int oracle_cost_volume_forward(const float *x, const float *y, float *cost,
+                                   int64_t N, int64_t C, int64_t Dm, int64_t H, int64_t W)
+{
+    const int64_t HW = H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t n = 0; n < N; n++)
+        for (int64_t c = 0; c < 2 * C; c++)
+            for (int64_t i = 0; i < Dm; i++)
+                for (int64_t h = 0; h < H; h++)
+                    for (int64_t w = 0; w < W; w++) {
+                        float v = 0.0f;
+                        if (w >= i)
+                            v = c < C ? x[(n * C + c) * HW + h * W + w]
+                                      : y[(n * C + (c - C)) * HW + h * W + (w - i)];
+                        cost[(((n * 2 * C + c) * Dm + i) * H + h) * W + w] = v;
+                    }
+    return 0;
+}
+
+/* adjoint of the slice assignments (autograd CopySlices) */
+API int oracle_cost_volume_backward(const float *gcost, float *gx, float *gy,
+                                    int64_t N, int64_t C, int64_t Dm, int64_t H, int64_t W)
+{
+    const int64_t HW = H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t n = 0; n < N; n++)
+        for (int64_t c = 0; c < C; c++)
+            for (int64_t h = 0; h < H; h++)
+                for (int64_t w = 0; w < W; w++) {
+                    float ax = 0.0f, ay = 0.0f;
+                    for (int64_t i = 0; i < Dm; i++) {
+                        if (w >= i)
+                            ax += gcost[(((n * 2 * C + c) * Dm + i) * H + h) * W + w];
+                        if (w + i < W)
+                            ay += gcost[(((n * 2 * C + C + c) * Dm + i) * H + h) * W + w + i];
+                    }
+                    gx[(n * C + c) * HW + h * W + w] = ax;
+                    gy[(n * C + c) * HW + h * W + w] = ay;
+                }
+    return 0;
+}
+
+/* ---- DisparityRegression (modules/GANet.py:142-148) ------------------------ */
+/* p: (N,Dm,H,W) -> disp: (N,H,W) = sum_d d * p[d]   (sequential fp32 sum) */
+API int oracle_disp_regression_forward(const float *p, float *disp,
+                                       int64_t N, int64_t Dm, int64_t H, int64_t W)
+{
+    const int64_t HW = H * W;
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < N; n++)
+        for (int64_t i = 0; i < HW; i++) {
+            float acc = 0.0f;
+            for (int64_t d = 0; d < Dm; d++) acc += p[(n * Dm + d) * HW + i] * (float)d;
+            disp[n * HW + i] = acc;
+        }
+    return 0;
+}
+
+API int oracle_disp_regression_backward(const float *gdisp, float *gp,
+                                        int64_t N, int64_t Dm, int64_t H, int64_t W)
+{
+    const int64_t HW = H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int64_t n = 0; n < N; n++)
+        for (int64_t d = 0; d < Dm; d++)
+            for (int64_t i = 0; i < HW; i++)
+                gp[(n * Dm + d) * HW + i] = gdisp[n * HW + i] * (float)d;
+    return 0;
+}
+
+API int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
