@@ -1,0 +1,526 @@
+#!/usr/bin/env python
+"""Benchmark of the GANet guided-aggregation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path -- SGA forward+backward and LGA2
+forward+backward -- over one synthetic batch B x C x D x H x W = 8 x 32 x 192 x
+240 x 624 (BASELINE.json; SURVEY.md 8d for the input recipe).  The batch axis is
+sharded over the ranks (no data-path collective: SURVEY.md 8e); on one GPU the
+batch is walked one sample at a time.  Rank 0 prints ONE JSON line.
+
+  value      voxels/s = (B*C*D*H*W + B*D*H*W) * K / max-over-ranks device time,
+             inputs resident in HBM, timed with CUDA events on the launch stream
+  e2e        the same work through the public nn.Module API starting from pinned
+             HOST buffers, results copied back to the host, copies inside the
+             timed region
+  roofline   algorithmic bytes of the dominant op (SGA fwd+bwd: 22 + 240/D bytes per
+             voxel) / its device time / measured HBM peak
+  cpu_baseline  the reference's own kernel bodies on the host cores (oracle/_ref) on
+             a bounded sample; a reported baseline, not the target
+
+`--impl reference` times that CPU reference arm alone on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SGA+LGA cost-volume voxels/sec (fwd+bwd) at D=192 HxW=240x624; HBM %peak"
+HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ---- arithmetic shared with tests/test_host.py ---------------------------------
+def shard_samples(batch, world, rank):
+    """Contiguous batch shard of rank `rank` (rank r owns [r*B/G, (r+1)*B/G))."""
+    lo = batch * rank // world
+    hi = batch * (rank + 1) // world
+    return list(range(lo, hi))
+
+
+def sga_bytes_per_voxel(D):
+    """SGA fwd (9 + 80/D) + bwd (13 + 160/D) algorithmic bytes per voxel."""
+    return 22.0 + 240.0 / D
+
+
+def lga2_bytes_per_voxel(D):
+    """LGA2 fwd (8 + 300/D) + bwd (12 + 600/D) algorithmic bytes per voxel."""
+    return 20.0 + 900.0 / D
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--channels", type=int, default=32)
+    ap.add_argument("--depth", type=int, default=192)
+    ap.add_argument("--height", type=int, default=240)
+    ap.add_argument("--width", type=int, default=624)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0,
+                    help="target CPU time of the bounded cpu_baseline sample")
+    return ap.parse_args()
+
+
+def load_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """DRAM bytes per voxel of the dominant op from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- the reference's CPU implementation (oracle/_ref, else the oracle port) -------
+def cpu_reference_rates(depth, height, width, seconds):
+    """Time SGA fwd+bwd and LGA2 fwd+bwd of the reference's own kernel bodies on the
+    host cores on a bounded sample; returns voxel rates and a description."""
+    import numpy as np
+    from oracle import api as port
+    from oracle import ref_cpu
+    use_ref = ref_cpu.available()
+    rng = np.random.default_rng(0)
+
+    def l1(a, axis):
+        return (a / np.abs(a).sum(axis=axis, keepdims=True)).astype(np.float32)
+
+    def sga_once(shape):
+        N, C, D, H, W = shape
+        x = rng.standard_normal(shape).astype(np.float32)
+        g = [l1(rng.standard_normal((N, C, 5, H, W)), 2) for _ in range(4)]
+        go = rng.standard_normal(shape).astype(np.float32)
+        t0 = time.perf_counter()
+        if use_ref:
+            out, mask, temp = ref_cpu.sga_forward(x, *g)
+            ref_cpu.sga_backward(x, *g, temp, mask, go)
+        else:
+            out, mask = port.sga_forward(x, *g, fused=False)
+            port.sga_backward(x, *g, mask, go, fused=False)
+        return time.perf_counter() - t0
+
+    def lga_once(shape):
+        x = rng.standard_normal(shape).astype(np.float32)
+        f = l1(rng.standard_normal((shape[0], 75) + shape[2:]), 1)
+        go = rng.standard_normal(shape).astype(np.float32)
+        t0 = time.perf_counter()
+        if use_ref:
+            y, y1 = ref_cpu.lga2_forward(x, f)
+            ref_cpu.lga2_backward(x, f, y1, go)
+        else:
+            y, tmp = port.lga_forward(x, f, 2, 2)
+            port.lga_backward(x, f, tmp, go, 2, 2)
+        return time.perf_counter() - t0
+
+    # calibrate on a thin slab of ONE (n,c) slice at the real D and W, then size the
+    # sample (rows of that slice) for ~seconds of CPU work
+    cores = os.cpu_count() or 1
+    H, W = height, width
+    cal = (1, 1, depth, min(H, 16), W)
+    rate = np.prod(cal) / sga_once(cal)
+    hs = int(max(min(H, 16), min(H, rate * seconds * 0.6 / (depth * W))))
+    sga_shape = (1, 1, depth, hs, W)
+    t_sga = sga_once(sga_shape)
+    r_sga = float(np.prod(sga_shape) / t_sga)
+    lcal = (1, depth, min(H, 8), W)
+    lrate = np.prod(lcal) / lga_once(lcal)
+    hl = int(max(min(H, 8), min(H, lrate * seconds * 0.4 / (depth * W))))
+    lga_shape = (1, depth, hl, W)
+    t_lga = lga_once(lga_shape)
+    r_lga = float(np.prod(lga_shape) / t_lga)
+    return {
+        "r_sga": r_sga, "r_lga": r_lga, "cores": cores,
+        "threads": port.num_threads(),
+        "kind": "reference" if use_ref else "port",
+        "sample": "SGA fwd+bwd on %s in %.1fs + LGA2 fwd+bwd on %s in %.1fs, rates combined in "
+                  "the workload's voxel proportions" % ("x".join(map(str, sga_shape)), t_sga,
+                                                       "x".join(map(str, lga_shape)), t_lga),
+    }
+
+
+def combine_rates(v_sga, v_lga, r_sga, r_lga):
+    return (v_sga + v_lga) / (v_sga / r_sga + v_lga / r_lga)
+
+
+def run_reference_arm(a):
+    """`--impl reference`: the reference's own CPU implementation of the path on the
+    host cores, K bounded steps after W warm-ups.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    B, C, D, H, W = a.batch, a.channels, a.depth, a.height, a.width
+    v_sga, v_lga = B * C * D * H * W, B * D * H * W
+    per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    vals, info = [], None
+    t_begin = time.perf_counter()
+    for i in range(a.warmup + a.steps):
+        info = cpu_reference_rates(D, H, W, per_step)
+        if i >= a.warmup:
+            vals.append(combine_rates(v_sga, v_lga, info["r_sga"], info["r_lga"]))
+    wall = time.perf_counter() - t_begin
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * (v_sga + v_lga) / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SGA+LGA2 fwd+bwd, B=%d C=%d D=%d HxW=%dx%d (CPU arm: bounded "
+                               "sample per step)" % (B, C, D, H, W)},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": info["cores"],
+                         "threads": info["threads"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm ------------------------------------------------------------------------
+def make_inputs(torch, dev, samples, C, D, H, W, seed):
+    """SURVEY.md 8d recipe, one sample at a time so peak memory stays bounded."""
+    import torch.nn.functional as F
+    n = len(samples)
+    x = torch.empty((n, C, D, H, W), device=dev)
+    go = torch.empty_like(x)
+    g = [torch.empty((n, C, 5, H, W), device=dev) for _ in range(4)]
+    xl = torch.empty((n, D, H, W), device=dev)
+    gol = torch.empty_like(xl)
+    fl = torch.empty((n, 75, H, W), device=dev)
+    gen = torch.Generator(device=dev)
+    for i, s in enumerate(samples):
+        gen.manual_seed(seed * 100003 + s)
+        x[i].normal_(generator=gen)
+        go[i].normal_(generator=gen)
+        for k in range(4):
+            g[k][i].normal_(generator=gen)
+            g[k][i] = F.normalize(g[k][i], p=1, dim=1)
+        xl[i].normal_(generator=gen)
+        gol[i].normal_(generator=gen)
+        fl[i].normal_(generator=gen)
+        fl[i] = F.normalize(fl[i], p=1, dim=0)
+    return x, go, g, xl, gol, fl
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from ganet_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, D, H, W = a.batch, a.channels, a.depth, a.height, a.width
+    mine = shard_samples(B, world, rank)
+    v_sga, v_lga = B * C * D * H * W, B * D * H * W
+    x, go, g, xl, gol, fl = make_inputs(torch, dev, mine, C, D, H, W, seed=0)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    phase_events = []
+
+    def one_sample(i, record):
+        s = slice(i, i + 1)
+        e = [ev() for _ in range(5)] if record else None
+        if record: e[0].record()
+        out, mask = ops.sga_forward(x[s], g[0][s], g[1][s], g[2][s], g[3][s])
+        if record: e[1].record()
+        gi, gg = ops.sga_backward(x[s], g[0][s], g[1][s], g[2][s], g[3][s], mask, go[s])
+        if record: e[2].record()
+        y1 = ops.lga_forward(xl[s], fl[s], 2)
+        y = ops.lga_forward(y1, fl[s], 2)
+        if record: e[3].record()
+        g1, gf = ops.lga_backward(y1, fl[s], gol[s], 2)
+        gx, gf = ops.lga_backward(xl[s], fl[s], g1, 2, grad_f=gf)
+        if record:
+            e[4].record()
+            phase_events.append(e)
+        return out, gi, gg, y, gx, gf
+
+    def step(record):
+        for i in range(len(mine)):
+            one_sample(i, record)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(False)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(a.steps):
+        step(True)
+    t1.record()
+    sync_all()
+    ms = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = (v_sga + v_lga) * a.steps / (ms * 1e-3)
+
+    # per-phase device time on this rank (events sit on the launch stream)
+    ph = [0.0, 0.0, 0.0, 0.0]
+    for e in phase_events:
+        for k in range(4):
+            ph[k] += e[k].elapsed_time(e[k + 1])
+    n_local = len(mine) * a.steps
+    local_v_sga = len(mine) * C * D * H * W
+    t_sga = (ph[0] + ph[1]) * 1e-3 / a.steps          # seconds per step on this rank
+    peak, peak_src = load_peak()
+    sga_gbs = sga_bytes_per_voxel(D) * local_v_sga / t_sga / 1e9 if t_sga > 0 else 0.0
+    traffic = load_traffic()
+
+    # launches of OUR kernels in the timed region: SGA fwd 4, SGA bwd 8 per workspace
+    # chunk, LGA2 fwd 2, LGA2 bwd 4 -- per sample per step
+    slice_bytes = 4 * D * H * W
+    slices_per_chunk = max(1, min(C, ops._workspace_budget() // slice_bytes))
+    ws_chunks = -(-C // slices_per_chunk)
+    launches = n_local * (4 + 8 * ws_chunks + 2 + 4)
+
+    # ---- end to end through the public modules, from pinned host buffers ---------
+    e2e = None
+    if not a.no_e2e and len(mine) > 0:
+        e2e = run_e2e(torch, dist, world, dev, a, mine, v_sga, v_lga)
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SGA fwd+bwd on %dx%dx%dx%dx%d + LGA2(r=2) fwd+bwd on %dx%dx%dx%d, "
+                                   "batch sharded over ranks, one sample per call"
+                                   % (B, C, D, H, W, B, D, H, W),
+                       "global_batch": B, "parallelism": "batch-shard x%d, no data-path collective" % world,
+                       "l2": "inputs larger than L2 (3.7 GB per sample, distinct per sample)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (4 + 8 scan launches per sample)",
+                         "achieved": sga_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": sga_gbs / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_voxel": sga_bytes_per_voxel(D),
+                         "traffic": traffic},
+            "phases_ms_per_step": {"sga_fwd": ph[0] / a.steps, "sga_bwd": ph[1] / a.steps,
+                                   "lga2_fwd": ph[2] / a.steps, "lga2_bwd": ph[3] / a.steps},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            info = cpu_reference_rates(D, H, W, a.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": combine_rates(v_sga, v_lga, info["r_sga"], info["r_lga"]),
+                "unit": "voxels/s", "cores": info["cores"], "threads": info["threads"],
+                "kind": info["kind"], "sample": info["sample"]}
+        if world == 1 and not a.no_ref_gpu:
+            del x, go
+            torch.cuda.empty_cache()
+            line["reference_cuda_on_this_gpu"] = ref_gpu_rate(torch, dev, C, D, H, W)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(torch, dist, world, dev, a, mine, v_sga, v_lga):
+    """Same work through the reference-facing nn.Modules with HOST buffers: per sample,
+    pinned host -> device copies of every input, forward + autograd backward, results
+    (outputs and all gradients) copied back to pinned host memory."""
+    import torch.nn.functional as F
+    from ganet_b200.modules import SGA, LGA2
+    C, D, H, W = a.channels, a.depth, a.height, a.width
+    sga, lga2 = SGA(), LGA2(2)
+    pin = lambda *s: torch.empty(s, pin_memory=True)    # noqa: E731
+
+    def host_randn(*s, norm_dim=None):      # generated on the device (fast), parked in pinned host memory
+        t = torch.randn(*s, device=dev)
+        if norm_dim is not None:
+            t = F.normalize(t, p=1, dim=norm_dim)
+        h = pin(*s)
+        h.copy_(t)
+        return h
+
+    hx, hgo = host_randn(1, C, D, H, W), host_randn(1, C, D, H, W)
+    hg = [host_randn(1, C, 5, H, W, norm_dim=2) for _ in range(4)]
+    hxl, hgol = host_randn(1, D, H, W), host_randn(1, D, H, W)
+    hfl = host_randn(1, 75, H, W, norm_dim=1)
+    r_out, r_gi = pin(1, C, D, H, W), pin(1, C, D, H, W)
+    r_gg = [pin(1, C, 5, H, W) for _ in range(4)]
+    r_y, r_gx, r_gf = pin(1, D, H, W), pin(1, D, H, W), pin(1, 75, H, W)
+    h2d = sum(t.numel() * 4 for t in [hx, hgo, hxl, hgol, hfl] + hg)
+    d2h = sum(t.numel() * 4 for t in [r_out, r_gi, r_y, r_gx, r_gf] + r_gg)
+
+    def one():
+        xd = hx.to(dev, non_blocking=True).requires_grad_()
+        gd = [t.to(dev, non_blocking=True).requires_grad_() for t in hg]
+        god = hgo.to(dev, non_blocking=True)
+        out = sga(xd, *gd)
+        out.backward(god)
+        r_out.copy_(out.detach(), non_blocking=True)
+        r_gi.copy_(xd.grad, non_blocking=True)
+        for dst, t in zip(r_gg, gd):
+            dst.copy_(t.grad, non_blocking=True)
+        xld = hxl.to(dev, non_blocking=True).requires_grad_()
+        fld = hfl.to(dev, non_blocking=True).requires_grad_()
+        gold = hgol.to(dev, non_blocking=True)
+        y = lga2(xld, fld)
+        y.backward(gold)
+        r_y.copy_(y.detach(), non_blocking=True)
+        r_gx.copy_(xld.grad, non_blocking=True)
+        r_gf.copy_(fld.grad, non_blocking=True)
+
+    steps = max(1, min(a.steps, 2))
+    one()                                     # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        for _i in mine:
+            one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    wall = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return {"value": (v_sga + v_lga) * steps / (ms * 1e-3), "unit": "voxels/s",
+            "h2d_bytes_per_step": h2d * len(mine) * world, "d2h_bytes_per_step": d2h * len(mine) * world,
+            "steps": steps, "ms_per_step": ms / steps, "wall_s": wall,
+            "api": "ganet_b200.modules.SGA / LGA2 + autograd, pinned host buffers"}
+
+
+def ref_gpu_rate(torch, dev, C, D, H, W):
+    """The UNMODIFIED reference CUDA kernels (oracle/_ref/GANet*.so) on this same GPU,
+    one sample, same inputs recipe -- the number the new kernels have to beat."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        return {"unavailable": "oracle/_ref/GANet*.so not built"}
+    import torch.nn.functional as F
+    try:
+        cc = C
+        while cc * D * H * W >= 2 ** 31:      # the reference indexes with int
+            cc //= 2
+        x = torch.randn(1, cc, D, H, W, device=dev)
+        go = torch.randn_like(x)
+        g = [F.normalize(torch.randn(1, cc, 5, H, W, device=dev), p=1, dim=2) for _ in range(4)]
+        xl = torch.randn(1, D, H, W, device=dev)
+        gol = torch.randn_like(xl)
+        fl = F.normalize(torch.randn(1, 75, H, W, device=dev), p=1, dim=1)
+
+        def once():
+            out, mask, temp = ref_gpu.sga_forward(x, *g)
+            ref_gpu.sga_backward(x, *g, temp, mask, go)
+
+        def once_lga():
+            y, y1 = ref_gpu.lga2_forward(xl, fl)
+            ref_gpu.lga2_backward(xl, fl, y1, gol)
+
+        once(); once_lga()
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(); once(); e[1].record(); once_lga(); e[2].record()
+        torch.cuda.synchronize()
+        t_sga, t_lga = e[0].elapsed_time(e[1]) * 1e-3, e[1].elapsed_time(e[2]) * 1e-3
+        v_sga, v_lga = cc * D * H * W, D * H * W
+        r_sga, r_lga = v_sga / t_sga, v_lga / t_lga
+        return {"value": combine_rates(C * D * H * W, D * H * W, r_sga, r_lga), "unit": "voxels/s",
+                "sga_ms_per_sample": t_sga * 1e3 * C / cc, "lga2_ms_per_sample": t_lga * 1e3,
+                "sample": "1x%dx%dx%dx%d SGA fwd+bwd, 1x%dx%dx%d LGA2 fwd+bwd, allocations included "
+                          "as in functions/GANet.py" % (cc, D, H, W, D, H, W)}
+    except Exception as exc:           # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

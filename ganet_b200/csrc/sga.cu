@@ -1,0 +1,526 @@
+// SGA (semi-global guided aggregation) for sm_100a -- scan kernels and C ABI.
+//
+// Reference being replaced: libs/GANet/src/GANet_kernel.cu
+//   sga_{down,up,right,left}_forward        :66-127, :285-346, :507-565, :720-778
+//   Max / get_temp_grad / MaxDepth          :23-64
+//   sga_*_data_backward, *_weight_backward  :129-281, :348-505, :567-718, :780-933
+//   host sequences sga_kernel_forward/backward :935-1129
+//
+// Design (DESIGN.md has the full story).  The reference gives every scan LINE to
+// one thread that walks H*D (or W*D) dependent global read-modify-writes.  Here a
+// scan line belongs to a GROUP of L lanes of one warp: lane j of the group keeps
+// the contiguous depth chunk d = K*j .. K*j+K-1 of the running row in registers,
+// chunk-edge neighbours travel by warp shuffle, and the running max over depth
+// -- the only cross-depth reduction of the forward recurrence, since
+// P[argmax P] == max P -- is one `redux.sync.max.f32` (CREDUX) for L == 32.
+// The four directions share one kernel: a direction is just (first pixel,
+// pixel step) of the line.
+//
+// Rounding.  `out` and `mask` must be bit-identical to the reference CUDA
+// build, so the forward step spells out the exact FMA-contraction pattern nvcc
+// 12.9 chose for the reference on sm_100a (audited again from
+// the SASS of the unmodified reference build):
+//     first scan step : five chained fma(x, w_k, acc), acc = +0
+//     later, even d   : fma, fma, mul+add, mul+add, fma
+//     later, odd  d   : fma, fma, fma,     mul+add, fma
+// K is always even, so the parity of d = K*j + i is the parity of the unrolled
+// index i and the choice is made at compile time.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ganet {
+
+enum { MODE_FIRST = 0, MODE_COMBINE = 1, MODE_RAW = 2 };
+
+constexpr int kWarpsPerBlock = 4;
+
+struct LineGeom {
+    int T;       // scan length
+    int NL;      // number of lines per slice
+    int lmul;    // first pixel = line * lmul + padd
+    int padd;
+    int pstep;   // pixel step per scan step
+};
+
+__host__ __device__ inline LineGeom line_geom(int dir, int H, int W)
+{
+    LineGeom q;
+    switch (dir) {
+    case 0: q.T = H; q.NL = W; q.lmul = 1; q.padd = 0; q.pstep = W; break;                 // down
+    case 1: q.T = H; q.NL = W; q.lmul = 1; q.padd = (H - 1) * W; q.pstep = -W; break;      // up
+    case 2: q.T = W; q.NL = H; q.lmul = W; q.padd = 0; q.pstep = 1; break;                 // right
+    default: q.T = W; q.NL = H; q.lmul = W; q.padd = W - 1; q.pstep = -1; break;           // left
+    }
+    return q;
+}
+
+// ---------------------------------------------------------------------------
+// forward scan of one direction
+//   MODE_FIRST   : out = A, mask = 0           (sga_kernel_forward :962-968)
+//   MODE_COMBINE : if (out < A) { out = A; mask = dir; }   (Max, :23-36)
+//   MODE_RAW     : out = A                     (recompute for backward / debug)
+// ---------------------------------------------------------------------------
+template <int K, int L, int MODE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sga_scan_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, float *out,
+                    uint8_t *mask, int dir, int D, int H, int W, long long n_slices,
+                    int groups_per_slice)
+{
+    static_assert(K % 2 == 0, "depth parity must be a compile-time property");
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long s = gwarp / groups_per_slice;
+    if (s >= n_slices) return;
+    const int grp = (int)(gwarp - s * groups_per_slice);
+    const int j = lane / G, gl = lane - j * G;
+    const int HW = H * W;
+    const LineGeom q = line_geom(dir, H, W);
+    int line = grp * G + gl;
+    const bool line_ok = line < q.NL;
+    line = line_ok ? line : q.NL - 1;      // surplus lanes shadow the last line, never store
+
+    const long long S = (long long)D * HW;
+    const float *xs = x + s * S;
+    const float *gs = g + s * 5ll * HW;
+    float *os = out + s * S;
+    uint8_t *ms = (MODE == MODE_RAW) ? nullptr : mask + s * S;
+
+    const int d0 = K * j;
+    int off[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) off[i] = min(d0 + i, D - 1) * HW;   // clamped: loads stay in range
+
+    int p = line * q.lmul + q.padd;
+    float P[K], xc[K], w[5];
+#pragma unroll
+    for (int i = 0; i < K; i++) { xc[i] = ld_nc(xs + off[i] + p); P[i] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = ld_nc(gs + k * HW + p);
+    float pmax = 0.f;
+
+    for (int t = 0; t < q.T; t++) {
+        // software prefetch of the next scan position
+        const int pn = p + q.pstep;
+        float xn[K], wn[5];
+        if (t + 1 < q.T) {
+#pragma unroll
+            for (int i = 0; i < K; i++) xn[i] = ld_nc(xs + off[i] + pn);
+#pragma unroll
+            for (int k = 0; k < 5; k++) wn[k] = ld_nc(gs + k * HW + pn);
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; i++) xn[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; k++) wn[k] = 0.f;
+        }
+
+        float A[K];
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                float a = __fmaf_rn(xc[i], w[0], 0.f);
+                a = __fmaf_rn(xc[i], w[1], a);
+                a = __fmaf_rn(xc[i], w[2], a);
+                a = __fmaf_rn(xc[i], w[3], a);
+                A[i] = __fmaf_rn(xc[i], w[4], a);
+            }
+        } else {
+            const float up = from_prev_chunk<L>(P[K - 1]);   // P[d0 - 1]
+            const float dn = from_next_chunk<L>(P[0]);       // P[d0 + K]
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const int d = d0 + i;
+                const float pm = (i == 0) ? up : P[i == 0 ? 0 : i - 1];
+                const float pp = (i == K - 1) ? dn : P[i == K - 1 ? K - 1 : i + 1];
+                const float s3 = (d + 1 < D) ? pp : xc[i];
+                float a = __fmaf_rn(xc[i], w[0], 0.f);
+                a = __fmaf_rn(P[i], w[1], a);
+                if (i & 1) {                                  // odd d: d-1 exists, fused
+                    a = __fmaf_rn(pm, w[2], a);
+                } else {                                      // even d: select, then mul + add
+                    const float s2 = (d >= 1) ? pm : xc[i];
+                    a = __fadd_rn(a, __fmul_rn(s2, w[2]));
+                }
+                a = __fadd_rn(a, __fmul_rn(s3, w[3]));
+                A[i] = __fmaf_rn(pmax, w[4], a);
+            }
+        }
+
+        float lm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if (d0 + i < D) lm = fmaxf(lm, A[i]);
+        pmax = group_max<L>(lm);
+
+        if (line_ok) {
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                if (d0 + i < D) {
+                    const int e = off[i] + p;
+                    if (MODE == MODE_FIRST) {
+                        os[e] = A[i];
+                        ms[e] = 0;
+                    } else if (MODE == MODE_COMBINE) {
+                        if (os[e] < A[i]) { os[e] = A[i]; ms[e] = (uint8_t)dir; }
+                    } else {
+                        os[e] = A[i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++) { P[i] = A[i]; xc[i] = xn[i]; }
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = wn[k];
+        p = pn;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward of one direction: reverse scan that
+// propagates T, emits gradInput and the five guidance gradients per pixel.
+// `a` is the recomputed aggregate of this direction (MODE_RAW pass above).
+// ---------------------------------------------------------------------------
+template <int K, int L>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sga_scan_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
+                    const float *__restrict__ a, const uint8_t *__restrict__ mask,
+                    const float *__restrict__ go, float *gi, float *__restrict__ gg,
+                    int32_t *__restrict__ max_idx, int dir, int accumulate, int D, int H, int W,
+                    long long n_slices, int groups_per_slice)
+{
+    static_assert(L >= 8, "five guidance gradients are written by lanes j = 0..4");
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long s = gwarp / groups_per_slice;
+    if (s >= n_slices) return;
+    const int grp = (int)(gwarp - s * groups_per_slice);
+    const int j = lane / G, gl = lane - j * G;
+    const int HW = H * W;
+    const LineGeom q = line_geom(dir, H, W);
+    int line = grp * G + gl;
+    const bool line_ok = line < q.NL;
+    line = line_ok ? line : q.NL - 1;
+
+    const long long S = (long long)D * HW;
+    const float *xs = x + s * S;
+    const float *as = a + s * S;
+    const float *gos = go + s * S;
+    const uint8_t *ms = mask + s * S;
+    float *gis = gi + s * S;
+    const float *gs = g + s * 5ll * HW;
+    float *ggs = gg + s * 5ll * HW;
+    int32_t *mis = max_idx ? max_idx + s * (long long)HW : nullptr;
+
+    const int d0 = K * j;
+    int off[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) off[i] = min(d0 + i, D - 1) * HW;
+
+    // first arg-max over depth of one row held as K values per lane
+    auto row_argmax = [&](const float (&r)[K], float &vmax) -> int {
+        float best = (d0 < D) ? r[0] : -INFINITY;
+        int bi = d0;
+#pragma unroll
+        for (int i = 1; i < K; i++)
+            if (d0 + i < D && r[i] > best) { best = r[i]; bi = d0 + i; }
+        vmax = group_max<L>(best);
+        return group_min<L>(best == vmax ? bi : 0x7fffffff);
+    };
+
+    int p = line * q.lmul + q.padd + (q.T - 1) * q.pstep;   // last scan position
+
+    if (mis) {   // the reference's MaxDepth covers every pixel, including the last row
+        float r[K], vm;
+#pragma unroll
+        for (int i = 0; i < K; i++) r[i] = ld_nc(as + off[i] + p);
+        const int k = row_argmax(r, vm);
+        if (line_ok && j == 0) mis[p] = k;
+    }
+
+    float Tn[K], wnx[5];
+#pragma unroll
+    for (int i = 0; i < K; i++) Tn[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; k++) wnx[k] = 0.f;
+    float sum_tn = 0.f;
+    int idx_cur = -1;            // arg-max of A at the current position (set one step earlier)
+
+    for (int t = q.T - 1; t >= 0; t--) {
+        const int pq = p - q.pstep;      // previous scan position (t - 1)
+        float xv[K], t0[K], ap[K], w[5];
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            const int e = off[i] + p;
+            xv[i] = ld_nc(xs + e);
+            const float gv = ld_nc(gos + e);
+            const uint8_t mv = ms[e];
+            t0[i] = (d0 + i < D && mv == dir) ? gv : 0.f;       // get_temp_grad :38-48
+            ap[i] = (t >= 1) ? ld_nc(as + off[i] + pq) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = ld_nc(gs + k * HW + p);
+
+        float tc[K];
+        if (t + 1 < q.T) {
+            const float up = from_prev_chunk<L>(Tn[K - 1]);     // T[d0-1, t+1]
+            const float dn = from_next_chunk<L>(Tn[0]);         // T[d0+K, t+1]
+            const float inj = sum_tn * wnx[4];                  // max-path term (:167-178)
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const int d = d0 + i;
+                const float tm = (i == 0) ? up : Tn[i == 0 ? 0 : i - 1];
+                const float tp = (i == K - 1) ? dn : Tn[i == K - 1 ? K - 1 : i + 1];
+                float v = t0[i];
+                v += Tn[i] * wnx[1];
+                if (d + 1 < D) v += tp * wnx[2];
+                if (d >= 1) v += tm * wnx[3];
+                if (d == idx_cur) v += inj;
+                tc[i] = (d < D) ? v : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; i++) tc[i] = t0[i];
+        }
+
+        // gradInput (:164, :177, :200-207)
+        if (line_ok) {
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const int d = d0 + i;
+                if (d < D) {
+                    float v = tc[i] * w[0];
+                    if (d == 0) v += tc[i] * w[2];
+                    if (d == D - 1) v += tc[i] * w[3];
+                    const int e = off[i] + p;
+                    gis[e] = accumulate ? gis[e] + v : v;
+                }
+            }
+        }
+
+        // guidance gradients (:210-281)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, st = 0.f, amax = 0.f;
+        int idx_prev = -1;
+        if (t >= 1) {
+            const float aup = from_prev_chunk<L>(ap[K - 1]);    // A[d0-1, t-1]
+            const float adn = from_next_chunk<L>(ap[0]);        // A[d0+K, t-1]
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const int d = d0 + i;
+                const float am = (i == 0) ? aup : ap[i == 0 ? 0 : i - 1];
+                const float apn = (i == K - 1) ? adn : ap[i == K - 1 ? K - 1 : i + 1];
+                s0 += tc[i] * xv[i];
+                st += tc[i];
+                s1 += tc[i] * ap[i];
+                s2 += tc[i] * ((d >= 1) ? am : xv[i]);
+                s3 += tc[i] * ((d + 1 < D) ? apn : xv[i]);
+            }
+            idx_prev = row_argmax(ap, amax);
+            if (mis && line_ok && j == 0) mis[pq] = idx_prev;
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; i++) { s0 += tc[i] * xv[i]; st += tc[i]; }
+        }
+        s0 = group_sum<L>(s0);
+        st = group_sum<L>(st);
+        if (t >= 1) {
+            s1 = group_sum<L>(s1);
+            s2 = group_sum<L>(s2);
+            s3 = group_sum<L>(s3);
+        }
+        if (line_ok && j < 5) {
+            const float s4 = st * amax;
+            const float v = j == 0 ? s0 : (t >= 1 ? (j == 1 ? s1 : j == 2 ? s2 : j == 3 ? s3 : s4) : 0.f);
+            ggs[j * HW + p] = v;
+        }
+
+#pragma unroll
+        for (int i = 0; i < K; i++) Tn[i] = tc[i];
+#pragma unroll
+        for (int k = 0; k < 5; k++) wnx[k] = w[k];
+        sum_tn = st;
+        idx_cur = idx_prev;
+        p = pq;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct Cfg { int K, L; };
+
+// compiled (K, L) pairs; K even.  L = 8 puts 4 adjacent lines in one warp,
+// L = 32 one line per warp.
+#define GANET_SGA_CFGS(X) \
+    X(2, 8) X(4, 8) X(6, 8) X(10, 8) X(12, 8) X(24, 8) \
+    X(2, 32) X(4, 32) X(6, 32) X(10, 32) X(16, 32) X(24, 32)
+
+static const Cfg kCfgs[] = {
+#define X(K_, L_) {K_, L_},
+    GANET_SGA_CFGS(X)
+#undef X
+};
+
+static bool pick_cfg(int D, bool vertical, Cfg *out)
+{
+    double best = -1;
+    Cfg pick{0, 0};
+    for (const Cfg &c : kCfgs) {
+        if (c.K * c.L < D) continue;
+        double eff = (double)D / (c.K * c.L);
+        // vertical scans like 4 adjacent pixels per warp (16-byte segments);
+        // horizontal scans like many independent warps
+        if (vertical == (c.L == 8)) eff *= 1.2;
+        if (eff > best) { best = eff; pick = c; }
+    }
+    if (best < 0) return false;
+    *out = pick;
+    return true;
+}
+
+template <int MODE>
+static int launch_fwd(Cfg c, const float *x, const float *g, float *out, uint8_t *mask, int dir,
+                      int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    const LineGeom q = line_geom(dir, H, W);
+    const int G = 32 / c.L;
+    const int gps = (q.NL + G - 1) / G;
+    const long long warps = n_slices * gps;
+    const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+#define X(K_, L_)                                                                           \
+    if (c.K == K_ && c.L == L_) {                                                           \
+        sga_scan_fwd_kernel<K_, L_, MODE><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>( \
+            x, g, out, mask, dir, D, H, W, n_slices, gps);                                  \
+    } else
+    GANET_SGA_CFGS(X) { return GANET_EUNSUPPORTED; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int launch_bwd(Cfg c, const float *x, const float *g, const float *a, const uint8_t *mask,
+                      const float *go, float *gi, float *gg, int32_t *max_idx, int dir,
+                      int accumulate, int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    const LineGeom q = line_geom(dir, H, W);
+    const int G = 32 / c.L;
+    const int gps = (q.NL + G - 1) / G;
+    const long long warps = n_slices * gps;
+    const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+#define X(K_, L_)                                                                        \
+    if (c.K == K_ && c.L == L_) {                                                        \
+        sga_scan_bwd_kernel<K_, L_><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(   \
+            x, g, a, mask, go, gi, gg, max_idx, dir, accumulate, D, H, W, n_slices, gps); \
+    } else
+    GANET_SGA_CFGS(X) { return GANET_EUNSUPPORTED; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int check_dims(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    if (N <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return GANET_EINVAL;
+    if (D > 768) return GANET_EUNSUPPORTED;
+    if (D * H * W >= (1ll << 31)) return GANET_EUNSUPPORTED;   // one slice is indexed with int
+    return GANET_OK;
+}
+
+}  // namespace ganet
+
+using namespace ganet;
+
+GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float *g_up,
+                                const float *g_right, const float *g_left, float *out,
+                                uint8_t *mask, int64_t N, int64_t C, int64_t D, int64_t H,
+                                int64_t W, ganet_stream_t stream)
+{
+    if (!x || !g_down || !g_up || !g_right || !g_left || !out || !mask) return GANET_EINVAL;
+    int rc = check_dims(N, C, D, H, W);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Cfg cv, ch;
+    if (!pick_cfg((int)D, true, &cv) || !pick_cfg((int)D, false, &ch)) return GANET_EUNSUPPORTED;
+    const long long ns = N * C;
+    rc = launch_fwd<MODE_FIRST>(cv, x, g_down, out, mask, 0, (int)D, (int)H, (int)W, ns, st);
+    if (rc) return rc;
+    rc = launch_fwd<MODE_COMBINE>(cv, x, g_up, out, mask, 1, (int)D, (int)H, (int)W, ns, st);
+    if (rc) return rc;
+    rc = launch_fwd<MODE_COMBINE>(ch, x, g_right, out, mask, 2, (int)D, (int)H, (int)W, ns, st);
+    if (rc) return rc;
+    return launch_fwd<MODE_COMBINE>(ch, x, g_left, out, mask, 3, (int)D, (int)H, (int)W, ns, st);
+}
+
+GANET_API int ganet_sga_direction(const float *x, const float *g, float *a, int dir, int64_t N,
+                                  int64_t C, int64_t D, int64_t H, int64_t W,
+                                  ganet_stream_t stream)
+{
+    if (!x || !g || !a || dir < 0 || dir > 3) return GANET_EINVAL;
+    int rc = check_dims(N, C, D, H, W);
+    if (rc) return rc;
+    Cfg c;
+    if (!pick_cfg((int)D, dir < 2, &c)) return GANET_EUNSUPPORTED;
+    return launch_fwd<MODE_RAW>(c, x, g, a, nullptr, dir, (int)D, (int)H, (int)W, N * C,
+                                (cudaStream_t)stream);
+}
+
+GANET_API size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H,
+                                                  int64_t W)
+{
+    (void)N; (void)C;
+    return (size_t)(D * H * W) * sizeof(float);
+}
+
+GANET_API size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H,
+                                                   int64_t W)
+{
+    return (size_t)(N * C * D * H * W) * sizeof(float);
+}
+
+GANET_API int ganet_sga_backward(const float *x, const float *g_down, const float *g_up,
+                                 const float *g_right, const float *g_left, const uint8_t *mask,
+                                 const float *grad_out, float *grad_in, float *gg_down,
+                                 float *gg_up, float *gg_right, float *gg_left, int32_t *max_idx,
+                                 void *workspace, size_t workspace_bytes, int64_t N, int64_t C,
+                                 int64_t D, int64_t H, int64_t W, ganet_stream_t stream)
+{
+    if (!x || !g_down || !g_up || !g_right || !g_left || !mask || !grad_out || !grad_in ||
+        !gg_down || !gg_up || !gg_right || !gg_left || !workspace)
+        return GANET_EINVAL;
+    int rc = check_dims(N, C, D, H, W);
+    if (rc) return rc;
+    const long long S = D * H * W, HW = H * W, ns = N * C;
+    const long long fit = (long long)(workspace_bytes / (S * sizeof(float)));
+    if (fit < 1) return GANET_EWORKSPACE;
+    const long long chunk = fit < ns ? fit : ns;
+    cudaStream_t st = (cudaStream_t)stream;
+    Cfg cv, ch;
+    if (!pick_cfg((int)D, true, &cv) || !pick_cfg((int)D, false, &ch)) return GANET_EUNSUPPORTED;
+    const float *g[4] = {g_down, g_up, g_right, g_left};
+    float *gg[4] = {gg_down, gg_up, gg_right, gg_left};
+    static const int order[4] = {3, 0, 1, 2};    // the reference's order (:1040, :1061, :1084, :1106)
+    float *a = (float *)workspace;
+    for (long long s0 = 0; s0 < ns; s0 += chunk) {
+        const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
+        for (int o = 0; o < 4; o++) {
+            const int dir = order[o];
+            const Cfg c = dir < 2 ? cv : ch;
+            rc = launch_fwd<MODE_RAW>(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, nullptr, dir, (int)D,
+                                      (int)H, (int)W, n, st);
+            if (rc) return rc;
+            rc = launch_bwd(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, mask + s0 * S,
+                            grad_out + s0 * S, grad_in + s0 * S, gg[dir] + s0 * 5 * HW,
+                            (max_idx && dir == 2) ? max_idx + s0 * HW : nullptr, dir, o > 0,
+                            (int)D, (int)H, (int)W, n, st);
+            if (rc) return rc;
+        }
+    }
+    return GANET_OK;
+}

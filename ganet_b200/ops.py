@@ -1,0 +1,144 @@
+"""Tensor-level wrappers over the C ABI (no autograd).  Every function takes and
+returns contiguous fp32 CUDA tensors, allocates its outputs with torch (device
+memory plumbing only) and enqueues on the current CUDA stream."""
+import os
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+_i64 = _lib._i64
+_int = _lib._int
+
+
+def _dims5(x):
+    if x.dim() != 5:
+        raise ValueError("expected a 5-D (N,C,D,H,W) tensor, got %s" % (tuple(x.shape),))
+    return [_i64(int(v)) for v in x.shape]
+
+
+def _workspace_budget():
+    return int(os.environ.get("GANET_B200_WORKSPACE_BYTES", str(6 << 30)))
+
+
+def sga_forward(x, g0, g1, g2, g3):
+    """-> out (N,C,D,H,W) f32, mask (N,C,D,H,W) u8"""
+    N, C, D, H, W = x.shape
+    for g in (g0, g1, g2, g3):
+        if tuple(g.shape) != (N, C, 5, H, W):
+            raise ValueError("guidance must be (N,C,5,H,W), got %s" % (tuple(g.shape),))
+    with torch.cuda.device_of(x):
+        out = torch.empty_like(x)
+        mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        check(_lib.lib().ganet_sga_forward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(out),
+                                           ptr(mask, torch.uint8), *_dims5(x), stream()))
+    return out, mask
+
+
+def sga_direction(x, g, direction):
+    """one directional aggregate (0 down, 1 up, 2 right, 3 left), no max-combine"""
+    with torch.cuda.device_of(x):
+        a = torch.empty_like(x)
+        check(_lib.lib().ganet_sga_direction(ptr(x), ptr(g), ptr(a), _int(direction), *_dims5(x),
+                                             stream()))
+    return a
+
+
+def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspace_bytes=None):
+    """-> grad_in, (gg0, gg1, gg2, gg3)[, max_idx int32 (N,C,H,W)]"""
+    N, C, D, H, W = x.shape
+    L = _lib.lib()
+    with torch.cuda.device_of(x):
+        gi = torch.empty_like(x)
+        gg = [torch.empty_like(g0) for _ in range(4)]
+        idx = torch.empty((N, C, H, W), dtype=torch.int32, device=x.device) if want_max_idx else None
+        dims = _dims5(x)
+        ws_min = L.ganet_sga_backward_workspace_min(*dims)
+        ws_best = L.ganet_sga_backward_workspace_best(*dims)
+        budget = _workspace_budget() if workspace_bytes is None else int(workspace_bytes)
+        ws_bytes = min(ws_best, max(ws_min, budget // ws_min * ws_min))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(L.ganet_sga_backward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3),
+                                   ptr(mask, torch.uint8), ptr(grad_out), ptr(gi), ptr(gg[0]),
+                                   ptr(gg[1]), ptr(gg[2]), ptr(gg[3]),
+                                   ptr(idx, torch.int32) if idx is not None else None,
+                                   ptr(ws, torch.uint8), _lib._sz(ws_bytes), *dims, stream()))
+    if want_max_idx:
+        return gi, tuple(gg), idx
+    return gi, tuple(gg)
+
+
+def _lga_dims(x, f, radius):
+    if x.dim() not in (4, 5):
+        raise ValueError("LGA input must be (N,D,H,W) or (N,C,D,H,W)")
+    lead = 1
+    for v in x.shape[:-3]:
+        lead *= int(v)
+    D, H, W = (int(v) for v in x.shape[-3:])
+    F = 3 * (2 * radius + 1) ** 2
+    if tuple(f.shape) != tuple(x.shape[:-3]) + (F, H, W):
+        raise ValueError("LGA filters must be %s, got %s" % (tuple(x.shape[:-3]) + (F, H, W),
+                                                            tuple(f.shape)))
+    return _i64(lead), _i64(D), _i64(H), _i64(W)
+
+
+def lga_forward(x, f, radius):
+    with torch.cuda.device_of(x):
+        y = torch.empty_like(x)
+        check(_lib.lib().ganet_lga_forward(ptr(x), ptr(f), ptr(y), *_lga_dims(x, f, radius),
+                                           _int(radius), stream()))
+    return y
+
+
+def lga_backward(x, f, grad_out, radius, grad_f=None):
+    """-> grad_x, grad_f.  If grad_f is given it is accumulated into (+=)."""
+    with torch.cuda.device_of(x):
+        gx = torch.empty_like(x)
+        acc = grad_f is not None
+        gf = grad_f if acc else torch.empty_like(f)
+        check(_lib.lib().ganet_lga_backward(ptr(x), ptr(f), ptr(grad_out), ptr(gx), ptr(gf),
+                                            _int(int(acc)), *_lga_dims(x, f, radius), _int(radius),
+                                            stream()))
+    return gx, gf
+
+
+def cost_volume_forward(x, y, maxdisp_plus1):
+    N, C, H, W = x.shape
+    if tuple(y.shape) != tuple(x.shape):
+        raise ValueError("left/right feature maps must have the same shape")
+    Dm = int(maxdisp_plus1)
+    with torch.cuda.device_of(x):
+        cost = torch.empty((N, 2 * C, Dm, H, W), dtype=x.dtype, device=x.device)
+        check(_lib.lib().ganet_cost_volume_forward(ptr(x), ptr(y), ptr(cost), _i64(N), _i64(C),
+                                                   _i64(Dm), _i64(H), _i64(W), stream()))
+    return cost
+
+
+def cost_volume_backward(grad_cost):
+    N, C2, Dm, H, W = grad_cost.shape
+    C = C2 // 2
+    with torch.cuda.device_of(grad_cost):
+        gx = torch.empty((N, C, H, W), dtype=grad_cost.dtype, device=grad_cost.device)
+        gy = torch.empty_like(gx)
+        check(_lib.lib().ganet_cost_volume_backward(ptr(grad_cost), ptr(gx), ptr(gy), _i64(N),
+                                                    _i64(C), _i64(Dm), _i64(H), _i64(W), stream()))
+    return gx, gy
+
+
+def disp_regression_forward(p):
+    N, Dm, H, W = p.shape
+    with torch.cuda.device_of(p):
+        out = torch.empty((N, H, W), dtype=p.dtype, device=p.device)
+        check(_lib.lib().ganet_disp_regression_forward(ptr(p), ptr(out), _i64(N), _i64(Dm), _i64(H),
+                                                       _i64(W), stream()))
+    return out
+
+
+def disp_regression_backward(grad_disp, Dm):
+    N, H, W = grad_disp.shape
+    with torch.cuda.device_of(grad_disp):
+        gp = torch.empty((N, Dm, H, W), dtype=grad_disp.dtype, device=grad_disp.device)
+        check(_lib.lib().ganet_disp_regression_backward(ptr(grad_disp), ptr(gp), _i64(N), _i64(Dm),
+                                                        _i64(H), _i64(W), stream()))
+    return gp

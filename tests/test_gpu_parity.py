@@ -1,0 +1,358 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI,
+against
+  (1) the UNMODIFIED reference CUDA extension (oracle/_ref/GANet*.so): SGA forward
+      values, direction mask and depth arg-max BIT-EXACT; gradients and LGA within
+      the north_star tolerance of 1e-4 relative fp32;
+  (2) the CPU oracle (oracle/ganet_oracle.c, fused rounding): same criteria;
+  (3) the committed golden vectors (tests/golden/, generated from the reference's
+      kernel bodies on the host; unfused rounding, hence tolerance not bit-exactness).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import api as oracle
+from oracle import ref_gpu
+from util import assert_close, lga_inputs, sga_inputs
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4          # north_star: 1e-4 relative fp32
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+needs_ref = pytest.mark.skipif(not ref_gpu.available(),
+                               reason="oracle/_ref/GANet*.so (reference CUDA extension) not built")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ganet_b200 import ops as o
+    return o
+
+
+# shapes: tiny edge cases (D=1, H=1, W=1, odd/even D, D not a multiple of the lane
+# chunking), config 1 of BASELINE.json, and the model's 1/6-resolution D=33
+SGA_SHAPES = [(2, 3, 7, 5, 6), (1, 2, 1, 4, 3), (1, 1, 2, 1, 5), (1, 2, 3, 6, 1), (1, 1, 1, 1, 1),
+              (1, 2, 9, 8, 10), (1, 1, 33, 9, 13), (1, 2, 65, 6, 11), (1, 1, 192, 5, 9),
+              (1, 1, 288, 3, 5), (1, 1, 100, 4, 35), (1, 8, 48, 48, 96)]
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", SGA_SHAPES)
+def test_sga_forward_bit_exact_vs_reference_cuda(ops, shape):
+    x, g, _ = sga_inputs(shape, seed=1 + sum(shape))
+    xt, gt = cu(x), [cu(a) for a in g]
+    out, mask = ops.sga_forward(xt, *gt)
+    ro, rm, rtemp = ref_gpu.sga_forward(xt, *gt)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ro), "SGA forward values differ from the reference CUDA kernels"
+    assert torch.equal(mask, rm.to(torch.uint8)), "direction mask differs"
+    assert torch.equal(ops.sga_direction(xt, gt[3], 3), rtemp), "left aggregate differs"
+
+
+@needs_ref
+@pytest.mark.parametrize("direction", [0, 1, 2, 3])
+def test_each_direction_bit_exact_vs_reference_cuda(ops, direction):
+    """Isolate one scan kernel of the reference: x in [1, 1.1) with positive weights
+    keeps every aggregate in [1, 1.1); scaling the guidance of `direction` by 1.2
+    lifts that aggregate above 1.2 everywhere, so it wins the max at every voxel and
+    `out` IS that direction's aggregate."""
+    shape = (1, 2, 12, 20, 24)
+    x, g, _ = sga_inputs(shape, seed=40 + direction, positive=True)
+    g[direction] = (g[direction] * 1.2).astype(np.float32)
+    xt, gt = cu(x), [cu(a) for a in g]
+    ro, rm, _ = ref_gpu.sga_forward(xt, *gt)
+    assert bool((rm == direction).all()), "construction failed: direction does not dominate"
+    mine = ops.sga_direction(xt, gt[direction], direction)
+    assert torch.equal(mine, ro)
+    out, mask = ops.sga_forward(xt, *gt)
+    assert torch.equal(out, ro) and torch.equal(mask, rm.to(torch.uint8))
+
+
+@pytest.mark.parametrize("shape", SGA_SHAPES)
+def test_sga_forward_bit_exact_vs_oracle(ops, shape):
+    x, g, _ = sga_inputs(shape, seed=2 + sum(shape))
+    out, mask = ops.sga_forward(cu(x), *[cu(a) for a in g])
+    oo, om, od = oracle.sga_forward(x, *g, fused=True, want_dirs=True)
+    assert np.array_equal(npy(out), oo)
+    assert np.array_equal(npy(mask), om)
+    for d in range(4):
+        assert np.array_equal(npy(ops.sga_direction(cu(x), cu(g[d]), d)), od[d])
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", SGA_SHAPES)
+def test_sga_backward_vs_reference_cuda(ops, shape):
+    x, g, go = sga_inputs(shape, seed=3 + sum(shape))
+    xt, gt, got = cu(x), [cu(a) for a in g], cu(go)
+    ro, rm, rtemp = ref_gpu.sga_forward(xt, *gt)
+    rgi, rgg, ridx = ref_gpu.sga_backward(xt, *gt, rtemp, rm, got)
+    out, mask = ops.sga_forward(xt, *gt)
+    gi, gg, idx = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True)
+    torch.cuda.synchronize()
+    assert torch.equal(idx, ridx.to(torch.int32)), "max_idx (depth arg-max) differs"
+    assert_close(npy(gi), npy(rgi), RTOL, "gradInput")
+    for d in range(4):
+        assert_close(npy(gg[d]), npy(rgg[d]), RTOL, "guidance grad %d" % d)
+
+
+@pytest.mark.parametrize("shape", SGA_SHAPES[:8])
+def test_sga_backward_vs_oracle(ops, shape):
+    x, g, go = sga_inputs(shape, seed=4 + sum(shape))
+    xt, gt = cu(x), [cu(a) for a in g]
+    out, mask = ops.sga_forward(xt, *gt)
+    gi, gg, idx = ops.sga_backward(xt, *gt, mask, cu(go), want_max_idx=True)
+    ogi, ogg, oidx = oracle.sga_backward(x, *g, npy(mask), go, fused=True)
+    assert np.array_equal(npy(idx), oidx)
+    assert_close(npy(gi), ogi, RTOL, "gradInput")
+    for d in range(4):
+        assert_close(npy(gg[d]), ogg[d], RTOL, "guidance grad %d" % d)
+
+
+def test_sga_backward_workspace_chunking_is_invisible(ops):
+    """Slices are independent: a one-slice workspace and a full one give the same bits."""
+    shape = (2, 3, 10, 7, 9)
+    x, g, go = sga_inputs(shape, seed=9)
+    xt, gt, got = cu(x), [cu(a) for a in g], cu(go)
+    out, mask = ops.sga_forward(xt, *gt)
+    a = ops.sga_backward(xt, *gt, mask, got, workspace_bytes=1)          # -> minimum: one slice
+    b = ops.sga_backward(xt, *gt, mask, got, workspace_bytes=1 << 30)
+    assert torch.equal(a[0], b[0])
+    assert all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+
+
+def test_sga_against_golden_vectors(ops):
+    z = np.load(os.path.join(GOLD, "sga_ref_cpu.npz"))
+    for k in range(int(z["n"])):
+        x, go = z[f"x{k}"], z[f"go{k}"]
+        g = [z[f"g{k}_{d}"] for d in range(4)]
+        xt, gt = cu(x), [cu(a) for a in g]
+        out, mask = ops.sga_forward(xt, *gt)
+        assert_close(npy(out), z[f"out{k}"], RTOL, "out")
+        # the golden vectors carry the host's unfused rounding: the mask may differ
+        # only where the two best directions are within rounding distance
+        bad = npy(mask) != z[f"mask{k}"]
+        assert bad.mean() <= 0.01
+        gi, gg = ops.sga_backward(xt, *gt, cu(z[f"mask{k}"]), cu(go))
+        assert_close(npy(gi), z[f"gi{k}"], RTOL, "gradInput")
+        for d in range(4):
+            assert_close(npy(gg[d]), z[f"gg{k}_{d}"], RTOL, "guidance grad")
+
+
+def test_sga_ties_and_constant_input(ops):
+    x = torch.full((1, 2, 6, 5, 7), 0.75, device="cuda")
+    g = [torch.full((1, 2, 5, 5, 7), 0.2, device="cuda") for _ in range(4)]
+    out, mask = ops.sga_forward(x, *g)
+    assert int(mask.max()) == 0                     # ties keep the lowest direction id
+    _, _, idx = ops.sga_backward(x, *g, mask, torch.ones_like(x), want_max_idx=True)
+    assert int(idx.max()) == 0                      # ties keep the lowest depth
+
+
+# ---- LGA ---------------------------------------------------------------------
+LGA_SHAPES = [(2, 7, 5, 6), (1, 3, 9, 11), (1, 1, 1, 1), (1, 5, 1, 40), (1, 4, 37, 3),
+              (1, 33, 20, 150), (2, 2, 3, 5, 4)]
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", LGA_SHAPES)
+def test_lga2_vs_reference_cuda(ops, shape):
+    x, f, go = lga_inputs(shape, seed=5)
+    xt, ft, got = cu(x), cu(f), cu(go)
+    ry, ry1 = ref_gpu.lga2_forward(xt, ft)
+    rgx, rgf = ref_gpu.lga2_backward(xt, ft, ry1, got)
+    y1 = ops.lga_forward(xt, ft, 2)
+    y = ops.lga_forward(y1, ft, 2)
+    g1, gf = ops.lga_backward(y1, ft, got, 2)
+    gx, gf = ops.lga_backward(xt, ft, g1, 2, grad_f=gf)
+    assert_close(npy(y1), npy(ry1), RTOL, "y1")
+    assert_close(npy(y), npy(ry), RTOL, "y")
+    assert_close(npy(gx), npy(rgx), RTOL, "grad_x")
+    assert_close(npy(gf), npy(rgf), RTOL, "grad_f")
+
+
+@pytest.mark.parametrize("shape", LGA_SHAPES)
+@pytest.mark.parametrize("radius", [2, 1, 0])
+def test_lga_vs_oracle(ops, shape, radius):
+    x, f, go = lga_inputs(shape, seed=6, radius=radius)
+    xt, ft, got = cu(x), cu(f), cu(go)
+    y = ops.lga_forward(xt, ft, radius)
+    oy, _ = oracle.lga_forward(x, f, radius, 1)
+    assert_close(npy(y), oy, RTOL, "y")
+    gx, gf = ops.lga_backward(xt, ft, got, radius)
+    ogx, ogf = oracle.lga_backward(x, f, None, go, radius, 1)
+    assert_close(npy(gx), ogx, RTOL, "grad_x")
+    assert_close(npy(gf), ogf, RTOL, "grad_f")
+
+
+def test_lga_against_golden_vectors(ops):
+    z = np.load(os.path.join(GOLD, "lga_ref_cpu.npz"))
+    from ganet_b200.functions import Lga2Function, Lga3d2Function
+    for k in range(int(z["n"])):
+        x = cu(z[f"x{k}"]).requires_grad_()
+        f = cu(z[f"f{k}"]).requires_grad_()
+        fn = Lga2Function if x.dim() == 4 else Lga3d2Function
+        y = fn.apply(x, f, 2)
+        y.backward(cu(z[f"go{k}"]))
+        assert_close(npy(y), z[f"y{k}"], RTOL, "y")
+        assert_close(npy(x.grad), z[f"gx{k}"], RTOL, "grad_x")
+        assert_close(npy(f.grad), z[f"gf{k}"], RTOL, "grad_f")
+
+
+# ---- cost volume / regression ---------------------------------------------------
+def _ref_cost_volume(x, y, dm):
+    """libs/GANet/modules/GANet.py:119-134 run as written (stock torch ops)."""
+    num, channels, height, width = x.size()
+    cost = x.new().resize_(num, channels * 2, dm, height, width).zero_()
+    for i in range(dm):
+        if i > 0:
+            cost[:, :channels, i, :, i:] = x[:, :, :, i:]
+            cost[:, channels:, i, :, i:] = y[:, :, :, :-i]
+        else:
+            cost[:, :channels, i, :, :] = x
+            cost[:, channels:, i, :, :] = y
+    return cost.contiguous()
+
+
+@pytest.mark.parametrize("shape,dm", [((2, 3, 4, 9), 6), ((1, 32, 10, 26), 65), ((1, 2, 3, 5), 9)])
+def test_cost_volume_bit_exact_vs_torch_slices(shape, dm):
+    from ganet_b200.modules import GetCostVolume
+    torch.manual_seed(0)
+    x = torch.randn(shape, device="cuda", requires_grad=True)
+    y = torch.randn(shape, device="cuda", requires_grad=True)
+    cost = GetCostVolume(dm - 1)(x, y)
+    x2, y2 = x.detach().clone().requires_grad_(), y.detach().clone().requires_grad_()
+    ref = _ref_cost_volume(x2, y2, dm)
+    assert torch.equal(cost, ref)                  # pure copy: bit-exact
+    gc = torch.randn_like(cost)
+    cost.backward(gc)
+    ref.backward(gc)
+    assert_close(npy(x.grad), npy(x2.grad), RTOL, "grad_x")
+    assert_close(npy(y.grad), npy(y2.grad), RTOL, "grad_y")
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 3, 5), (1, 193, 12, 40), (1, 1, 2, 2)])
+def test_disparity_regression_vs_torch(shape):
+    from ganet_b200.modules import DisparityRegression
+    torch.manual_seed(1)
+    p = torch.softmax(torch.randn(shape, device="cuda"), 1).requires_grad_()
+    out = DisparityRegression(shape[1] - 1)(p)
+    # modules/GANet.py:145-147 as written
+    disp = torch.arange(shape[1], device="cuda", dtype=torch.float32).reshape(1, -1, 1, 1)
+    disp = disp.repeat(p.size()[0], 1, p.size()[2], p.size()[3])
+    p2 = p.detach().clone().requires_grad_()
+    ref = torch.sum(p2 * disp, 1)
+    assert_close(npy(out), npy(ref), RTOL, "disparity")
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g)
+    assert torch.equal(p.grad, p2.grad)
+
+
+# ---- autograd / API behaviour -----------------------------------------------------
+def test_sga_module_autograd_matches_oracle():
+    from ganet_b200.modules import SGA
+    shape = (1, 2, 8, 6, 7)
+    x, g, go = sga_inputs(shape, seed=12)
+    xt = cu(x).requires_grad_()
+    gt = [cu(a).requires_grad_() for a in g]
+    out = SGA()(xt, *gt)
+    out.backward(cu(go), retain_graph=True)
+    gi1 = xt.grad.clone()
+    xt.grad = None
+    out.backward(cu(go))                     # backward twice: saved state is not clobbered
+    assert torch.equal(gi1, xt.grad)
+    oo, om = oracle.sga_forward(x, *g, fused=True)
+    ogi, ogg, _ = oracle.sga_backward(x, *g, om, go, fused=True)
+    assert np.array_equal(npy(out), oo)
+    assert_close(npy(gi1), ogi, RTOL, "gradInput")
+    for d in range(4):
+        assert_close(npy(gt[d].grad) / 2, ogg[d], RTOL, "guidance grad")   # accumulated twice
+
+
+def test_lga2_backward_leaves_grad_output_intact():
+    from ganet_b200.modules import LGA2
+    x, f, go = lga_inputs((1, 6, 7, 8), seed=13)
+    xt, ft = cu(x).requires_grad_(), cu(f).requires_grad_()
+    got = cu(go)
+    keep = got.clone()
+    LGA2(2)(xt, ft).backward(got)
+    assert torch.equal(got, keep)            # the reference overwrites it (functions/GANet.py:199)
+
+
+def test_non_default_stream_and_threads(ops):
+    """The reference launches on legacy stream 0 only; here the current stream is used
+    and two host threads may call concurrently (DataParallel pattern)."""
+    import threading
+    shape = (1, 2, 10, 12, 14)
+    x, g, _ = sga_inputs(shape, seed=14)
+    oo, om = oracle.sga_forward(x, *g, fused=True)
+    results = {}
+
+    def work(i):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            xt, gt = cu(x), [cu(a) for a in g]
+            for _ in range(3):
+                out, mask = ops.sga_forward(xt, *gt)
+            st.synchronize()
+            results[i] = (npy(out), npy(mask))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(2):
+        assert np.array_equal(results[i][0], oo) and np.array_equal(results[i][1], om)
+
+
+@needs_ref
+def test_legacy_native_surface_matches_reference_extension():
+    """ganet_b200.legacy_native honours the reference's buffer contract
+    (caller-zeroed buffers, accumulate, fp32 mask, temp_out = left aggregate)."""
+    from ganet_b200 import legacy_native as mine
+    ref = ref_gpu.module()
+    shape = (1, 2, 6, 5, 7)
+    x, g, go = sga_inputs(shape, seed=15)
+    xt, gt, got = cu(x), [cu(a) for a in g], cu(go)
+
+    def run(mod):
+        out, temp, mask = (torch.zeros_like(xt) for _ in range(3))
+        assert mod.sga_cuda_forward(xt, *gt, temp, out, mask) == 1
+        gi, tg = torch.zeros_like(xt), torch.zeros_like(xt)
+        gg = [torch.zeros_like(gt[0]) for _ in range(4)]
+        idx = torch.zeros(shape[0], shape[1], shape[3], shape[4], device="cuda")
+        assert mod.sga_cuda_backward(xt, *gt, temp.clone(), mask, idx, got, tg, gi, *gg) == 1
+        return out, temp, mask, gi, gg, idx
+
+    a, b = run(mine), run(ref)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[5], b[5])
+    assert_close(npy(a[3]), npy(b[3]), RTOL, "gradInput")
+    for p, q in zip(a[4], b[4]):
+        assert_close(npy(p), npy(q), RTOL, "guidance grad")
+    xl, fl, gol = lga_inputs((1, 5, 6, 7), seed=16)
+    xl, fl, gol = cu(xl), cu(fl), cu(gol)
+    ya, yb = torch.zeros_like(xl), torch.zeros_like(xl)
+    mine.lga_cuda_forward(xl, fl, ya, 2)
+    ref.lga_cuda_forward(xl, fl, yb, 2)
+    assert_close(npy(ya), npy(yb), RTOL, "lga forward")
+
+
+def test_error_reporting(ops):
+    x = torch.zeros(1, 1, 2, 3, 4, device="cuda")
+    g = torch.zeros(1, 1, 5, 3, 4, device="cuda")
+    with pytest.raises(ValueError):
+        ops.sga_forward(x, g, g, g, torch.zeros(1, 1, 4, 3, 4, device="cuda"))
+    with pytest.raises(TypeError):
+        ops.sga_forward(x.double(), g, g, g, g)
+    from ganet_b200.functions import SgaFunction
+    with pytest.raises(AssertionError):               # the reference's contiguity assert
+        SgaFunction.apply(x.transpose(3, 4), g, g, g, g)

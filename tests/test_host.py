@@ -1,0 +1,207 @@
+"""CPU tests of the host side: the C-ABI library loads and exports exactly what
+include/ganet_b200.h declares, the drop-in import surface resolves, the product
+path refuses to run without a GPU (no silent fallback), and the pure-Python
+pieces (losses, normalisation) match the reference's arithmetic."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native_so():
+    from ganet_b200 import build
+    return build.build()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ganet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ganet_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(native_so):
+    handle = ctypes.CDLL(native_so)
+    names = _declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(handle, n), "libganet_b200.so does not export " + n
+    from ganet_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names      # the Python binding covers the whole header
+    handle.ganet_abi_version.restype = ctypes.c_int
+    assert handle.ganet_abi_version() == 1
+    handle.ganet_error_string.restype = ctypes.c_char_p
+    assert b"workspace" in handle.ganet_error_string(-3)
+
+
+def test_library_contains_only_sm100a_code(native_so):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", native_so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_validation_without_gpu(native_so):
+    """Argument errors are reported before any CUDA call, so this runs on CPU."""
+    from ganet_b200 import _lib
+    L = _lib.lib()
+    i64 = ctypes.c_int64
+    assert L.ganet_sga_forward(None, None, None, None, None, None, None,
+                               i64(1), i64(1), i64(1), i64(1), i64(1), None) == -1
+    dummy = ctypes.c_void_p(16)
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy,
+                               i64(1), i64(1), i64(1000), i64(1), i64(1), None) == -2   # D > 768
+    assert L.ganet_sga_backward_workspace_min(i64(2), i64(3), i64(4), i64(5), i64(6)) == 4 * 5 * 6 * 4
+    assert L.ganet_sga_backward_workspace_best(i64(2), i64(3), i64(4), i64(5), i64(6)) == 6 * 120 * 4
+    d2 = ctypes.c_void_p(32)
+    assert L.ganet_lga_forward(dummy, dummy, d2, i64(1), i64(1), i64(1), i64(1), 9, None) == -2
+    assert L.ganet_lga_forward(dummy, dummy, dummy, i64(1), i64(1), i64(1), i64(1), 2, None) == -1   # y aliases x
+
+
+def test_product_path_refuses_cpu_tensors(native_so):
+    """No CPU fallback: CPU tensors raise instead of silently computing elsewhere."""
+    from ganet_b200 import _lib, modules
+    x = torch.zeros(1, 1, 2, 3, 4)
+    g = torch.zeros(1, 1, 5, 3, 4)
+    with pytest.raises(_lib.GanetNativeError):
+        modules.SGA()(x, g, g, g, g)
+    with pytest.raises(_lib.GanetNativeError):
+        modules.LGA2(2)(torch.zeros(1, 3, 4, 5), torch.zeros(1, 75, 4, 5))
+    with pytest.raises(_lib.GanetNativeError):
+        modules.DisparityRegression(2)(torch.zeros(1, 3, 4, 5))
+    with pytest.raises(_lib.GanetNativeError):
+        modules.GetCostVolume(2)(torch.zeros(1, 3, 4, 5), torch.zeros(1, 3, 4, 5))
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ganet_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text, \
+                    "%s mentions the oracle" % f
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "libs")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read()
+
+
+def test_reference_import_surface():
+    """Every name the reference's consumers import resolves (models/GANet_deep.py:4-8,
+    train.py:5), with the reference's constructor signatures."""
+    from libs.GANet.modules.GANet import (SGA, LGA, LGA2, LGA3, LGA3D, LGA3D2, LGA3D3,  # noqa: F401
+                                          DisparityRegression, GetCostVolume, MyLoss, MyLoss2,
+                                          MyNormalize)
+    from libs.GANet.functions.GANet import (SgaFunction, Lga2Function, Lga3Function,  # noqa: F401
+                                            LgaFunction, Lga3dFunction, Lga3d2Function,
+                                            Lga3d3Function, MyLoss2Function, MyLossFunction, GANet)
+    from libs.sync_bn.modules.sync_bn import BatchNorm2d, BatchNorm3d
+    assert GetCostVolume(64).maxdisp == 65 and DisparityRegression(192).maxdisp == 193
+    assert LGA2(radius=2).radius == 2 and LGA3(2).radius == 2 and LGA(2).radius == 2
+    assert len(list(SGA().parameters())) == 0 and len(SGA().state_dict()) == 0
+    assert sorted(BatchNorm3d(4).state_dict()) == ["bias", "num_batches_tracked", "running_mean",
+                                                   "running_var", "weight"]
+    assert isinstance(BatchNorm2d(4), torch.nn.BatchNorm2d)
+    for name in ("sga_cuda_forward", "sga_cuda_backward", "lga_cuda_forward", "lga_cuda_backward",
+                 "lga3d_cuda_forward", "lga3d_cuda_backward"):
+        assert callable(getattr(GANet, name))         # GANet_cuda.cpp:67-75
+    from libs.GANet.build.lib import GANet as G2
+    assert G2 is GANet
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_reference_models_construct_unchanged():
+    """models/GANet_deep.py and GANet11.py import and build on the new modules; the
+    parameter counts are the reference's."""
+    sys.path.append("/root/reference")
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        from models.GANet_deep import GANet as Deep
+        from models.GANet11 import GANet as G11
+        deep, g11 = Deep(192), G11(192)
+        assert sum(p.numel() for p in deep.parameters()) == 6580112
+        assert sum(p.numel() for p in g11.parameters()) == 4483728
+        assert len(deep.state_dict()) == 479 and len(g11.state_dict()) == 364
+        import ganet_b200.modules as M
+        assert isinstance(deep.cost_agg.sga1.SGA, M.SGA)
+        assert isinstance(deep.cv, M.GetCostVolume)
+    finally:
+        sys.path.remove("/root/reference")
+
+
+def _ref_myloss2(input1, input2, thresh=1, alpha=2):
+    """MyLoss2Function restated with the reference's in-place masked updates
+    (functions/GANet.py:266-289) as the checker for the functional port."""
+    diff = input1 - input2
+    temp = torch.abs(diff)
+    temp[temp < thresh] = temp[temp < thresh] ** 2 / thresh
+    tag = (temp <= thresh + alpha) & (temp >= thresh)
+    temp[tag] = temp[tag] * 2 - (temp[tag] - thresh) ** 2 / (2.0 * alpha) - thresh
+    temp[temp > thresh + alpha] += (alpha / 2.0)
+    loss = torch.mean(temp)
+    scale = torch.abs(diff)
+    scale[scale > thresh + alpha] = 1
+    tag = (scale <= thresh + alpha) & (scale >= thresh)
+    scale[tag] = 2 - (scale[tag] - thresh) / alpha
+    tag = scale < thresh
+    scale[tag] = 2 * scale[tag] / thresh
+    d = diff.clone()
+    d[d > 0] = 1.0
+    d[d < 0] = -1.0
+    return loss, d * scale / scale.numel()
+
+
+def test_myloss2_matches_reference_arithmetic():
+    from ganet_b200.modules import MyLoss2
+    torch.manual_seed(0)
+    a = (torch.randn(4, 9, 11) * 3).requires_grad_()
+    b = torch.randn(4, 9, 11)
+    loss = MyLoss2(1, 2)(a, b)
+    loss.backward()
+    ref_loss, ref_grad = _ref_myloss2(a.detach(), b)
+    assert torch.allclose(loss, ref_loss, rtol=1e-6)
+    assert torch.allclose(a.grad, ref_grad, rtol=1e-6, atol=1e-9)
+
+
+def test_myloss_and_mynormalize():
+    from ganet_b200.modules import MyLoss, MyNormalize
+    torch.manual_seed(1)
+    a = (torch.randn(3, 50) * 4).requires_grad_()
+    b = torch.randn(3, 50)
+    loss = MyLoss()(a, b)
+    assert torch.allclose(loss, (a - b).abs().mean())
+    loss.backward()
+    diff = (a - b).detach()
+    s = diff.abs()
+    s = torch.where(s > 5, torch.ones_like(s), s)
+    s = torch.where((s <= 5) & (s >= 1), 2 - (s - 3).abs() / 2, s)
+    assert torch.allclose(a.grad, torch.sign(diff) * s)
+    x = torch.randn(2, 5, 3)
+    x[0, :, 0] = 0
+    y = MyNormalize(1)(x)
+    n = x.abs().sum(1, keepdim=True)
+    assert torch.allclose(y[:, :, 1:], (x / (n + 1e-6))[:, :, 1:])
+    assert torch.all(y[0, :, 0] == 0)
+
+
+def test_bench_shard_plan_and_roofline_arithmetic():
+    import bench
+    assert bench.shard_samples(8, 1, 0) == list(range(8))
+    assert bench.shard_samples(8, 8, 3) == [3]
+    assert bench.shard_samples(8, 4, 3) == [6, 7]
+    got = sorted(s for r in range(2) for s in bench.shard_samples(8, 2, r))
+    assert got == list(range(8))
+    # SGA fwd+bwd = 22 + 240/D bytes per voxel, LGA2 = 20 + 900/D
+    assert abs(bench.sga_bytes_per_voxel(192) - 23.25) < 1e-9
+    assert abs(bench.lga2_bytes_per_voxel(192) - 24.6875) < 1e-9
