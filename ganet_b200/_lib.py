@@ -21,7 +21,9 @@ _sz = ctypes.c_size_t
 _SIGNATURES = {
     "ganet_abi_version": (_int, []),
     "ganet_error_string": (ctypes.c_char_p, [_int]),
-    "ganet_sga_forward": (_int, [_vp] * 7 + [_i64] * 5 + [_vp]),
+    "ganet_sga_forward": (_int, [_vp] * 8 + [_sz] + [_i64] * 5 + [_vp]),
+    "ganet_sga_forward_workspace_min": (_sz, [_i64] * 5),
+    "ganet_sga_forward_workspace_best": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_min": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_best": (_sz, [_i64] * 5),
     "ganet_sga_backward": (_int, [_vp] * 14 + [_sz] + [_i64] * 5 + [_vp]),

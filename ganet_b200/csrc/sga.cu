@@ -28,6 +28,9 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "sga_step.cuh"
+#include "sga_vert.cuh"
+#include "transpose.cuh"
 
 namespace ganet {
 
@@ -118,41 +121,13 @@ sga_scan_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
 
         float A[K];
         if (t == 0) {
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                float a = __fmaf_rn(xc[i], w[0], 0.f);
-                a = __fmaf_rn(xc[i], w[1], a);
-                a = __fmaf_rn(xc[i], w[2], a);
-                a = __fmaf_rn(xc[i], w[3], a);
-                A[i] = __fmaf_rn(xc[i], w[4], a);
-            }
+            sga_first_step<K>(xc, w, A);
         } else {
             const float up = from_prev_chunk<L>(P[K - 1]);   // P[d0 - 1]
             const float dn = from_next_chunk<L>(P[0]);       // P[d0 + K]
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                const int d = d0 + i;
-                const float pm = (i == 0) ? up : P[i == 0 ? 0 : i - 1];
-                const float pp = (i == K - 1) ? dn : P[i == K - 1 ? K - 1 : i + 1];
-                const float s3 = (d + 1 < D) ? pp : xc[i];
-                float a = __fmaf_rn(xc[i], w[0], 0.f);
-                a = __fmaf_rn(P[i], w[1], a);
-                if (i & 1) {                                  // odd d: d-1 exists, fused
-                    a = __fmaf_rn(pm, w[2], a);
-                } else {                                      // even d: select, then mul + add
-                    const float s2 = (d >= 1) ? pm : xc[i];
-                    a = __fadd_rn(a, __fmul_rn(s2, w[2]));
-                }
-                a = __fadd_rn(a, __fmul_rn(s3, w[3]));
-                A[i] = __fmaf_rn(pmax, w[4], a);
-            }
+            sga_next_step<K>(P, xc, w, up, dn, pmax, d0, D, A);
         }
-
-        float lm = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < K; i++)
-            if (d0 + i < D) lm = fmaxf(lm, A[i]);
-        pmax = group_max<L>(lm);
+        pmax = group_max<L>(chunk_max<K>(A, d0, D));
 
         if (line_ok) {
 #pragma unroll
@@ -425,6 +400,64 @@ static int launch_bwd(Cfg c, const float *x, const float *g, const float *a, con
     return GANET_OK;
 }
 
+// ---- vertical (coalesced) kernels: (K, MAXW) instantiations -------------------------
+#define GANET_VERT_CFGS(X) X(2, 16) X(4, 16) X(6, 16) X(12, 16) X(24, 12)
+
+struct VCfg { int K, NW; };
+
+static bool pick_vert_cfg(int D, VCfg *out)
+{
+    static const int ks[] = {2, 4, 6, 12, 24};
+    static const int mw[] = {16, 16, 16, 16, 12};
+    for (int i = 0; i < 5; i++) {
+        const int nw = (D + ks[i] - 1) / ks[i];
+        if (nw <= mw[i]) { out->K = ks[i]; out->NW = nw; return true; }
+    }
+    return false;       // D > 288: the line kernels take over
+}
+
+template <int MODE>
+static int launch_vert_fwd(VCfg c, const float *x, const float *g, float *out, uint8_t *mask,
+                           int dir, MaskIds ids, int D, int H, int W, long long n_slices,
+                           cudaStream_t st)
+{
+    const int strips = (W + 31) / 32;
+    const long long blocks = n_slices * strips;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const size_t smem = (size_t)2 * 3 * c.NW * 32 * sizeof(float);
+#define X(K_, W_)                                                                            \
+    if (c.K == K_) {                                                                         \
+        sga_vert_fwd_kernel<K_, W_, MODE><<<(unsigned)blocks, c.NW * 32, smem, st>>>(        \
+            x, g, out, mask, dir, ids, D, H, W, strips);                                     \
+    } else
+    GANET_VERT_CFGS(X) { return GANET_EUNSUPPORTED; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int launch_vert_bwd(VCfg c, const float *x, const float *g, const float *a,
+                           const uint8_t *mask, const float *go, float *gi, float *gg, int dir,
+                           int mask_id, int accumulate, int D, int H, int W, long long n_slices,
+                           cudaStream_t st)
+{
+    const int strips = (W + 31) / 32;
+    const long long blocks = n_slices * strips;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const size_t smem = (size_t)2 * NBW * c.NW * 32 * sizeof(float);
+#define X(K_, W_)                                                                            \
+    if (c.K == K_) {                                                                         \
+        sga_vert_bwd_kernel<K_, W_><<<(unsigned)blocks, c.NW * 32, smem, st>>>(              \
+            x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W, strips);           \
+    } else
+    GANET_VERT_CFGS(X) { return GANET_EUNSUPPORTED; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
 static int check_dims(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
     if (N <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return GANET_EINVAL;
@@ -437,25 +470,125 @@ static int check_dims(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 
 using namespace ganet;
 
+// ---- workspace carving ------------------------------------------------------------
+static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct FwdWs { size_t xT, outT, maskT, gT2, gT3, total; };
+static FwdWs fwd_ws(long long n, long long S, long long HW)
+{
+    FwdWs w; size_t o = 0;
+    w.xT = o;    o += align_up((size_t)n * S * 4);
+    w.outT = o;  o += align_up((size_t)n * S * 4);
+    w.maskT = o; o += align_up((size_t)n * S);
+    w.gT2 = o;   o += align_up((size_t)n * 5 * HW * 4);
+    w.gT3 = o;   o += align_up((size_t)n * 5 * HW * 4);
+    w.total = o;
+    return w;
+}
+
+struct BwdWs { size_t a, xT, goT, maskT, giT, gT, ggT, total; };
+static BwdWs bwd_ws(long long n, long long S, long long HW)
+{
+    BwdWs w; size_t o = 0;
+    w.a = o;     o += align_up((size_t)n * S * 4);
+    w.xT = o;    o += align_up((size_t)n * S * 4);
+    w.goT = o;   o += align_up((size_t)n * S * 4);
+    w.maskT = o; o += align_up((size_t)n * S);
+    w.giT = o;   o += align_up((size_t)n * S * 4);
+    w.gT = o;    o += align_up((size_t)n * 5 * HW * 4);
+    w.ggT = o;   o += align_up((size_t)n * 5 * HW * 4);
+    w.total = o;
+    return w;
+}
+
+// largest slice count whose workspace fits (0 if not even one)
+template <class F>
+static long long fit_slices(F sizer, size_t bytes, long long ns)
+{
+    if (sizer(1) > bytes) return 0;
+    long long lo = 1, hi = ns;
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) / 2;
+        if (sizer(mid) <= bytes) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+GANET_API size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    (void)N; (void)C;
+    return fwd_ws(1, D * H * W, H * W).total;
+}
+GANET_API size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    return fwd_ws(N * C, D * H * W, H * W).total;
+}
+GANET_API size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    (void)N; (void)C;
+    return bwd_ws(1, D * H * W, H * W).total;
+}
+GANET_API size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    return bwd_ws(N * C, D * H * W, H * W).total;
+}
+
+// slow generic path: one warp group per scan line, any D <= 768, no workspace
+static int sga_forward_lines(const float *x, const float *const g[4], float *out, uint8_t *mask,
+                             int D, int H, int W, long long ns, cudaStream_t st)
+{
+    Cfg cv, ch;
+    if (!pick_cfg(D, true, &cv) || !pick_cfg(D, false, &ch)) return GANET_EUNSUPPORTED;
+    int rc = launch_fwd<MODE_FIRST>(cv, x, g[0], out, mask, 0, D, H, W, ns, st);
+    if (rc) return rc;
+    rc = launch_fwd<MODE_COMBINE>(cv, x, g[1], out, mask, 1, D, H, W, ns, st);
+    if (rc) return rc;
+    rc = launch_fwd<MODE_COMBINE>(ch, x, g[2], out, mask, 2, D, H, W, ns, st);
+    if (rc) return rc;
+    return launch_fwd<MODE_COMBINE>(ch, x, g[3], out, mask, 3, D, H, W, ns, st);
+}
+
 GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float *g_up,
                                 const float *g_right, const float *g_left, float *out,
-                                uint8_t *mask, int64_t N, int64_t C, int64_t D, int64_t H,
-                                int64_t W, ganet_stream_t stream)
+                                uint8_t *mask, void *workspace, size_t workspace_bytes, int64_t N,
+                                int64_t C, int64_t D, int64_t H, int64_t W, ganet_stream_t stream)
 {
     if (!x || !g_down || !g_up || !g_right || !g_left || !out || !mask) return GANET_EINVAL;
     int rc = check_dims(N, C, D, H, W);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    Cfg cv, ch;
-    if (!pick_cfg((int)D, true, &cv) || !pick_cfg((int)D, false, &ch)) return GANET_EUNSUPPORTED;
-    const long long ns = N * C;
-    rc = launch_fwd<MODE_FIRST>(cv, x, g_down, out, mask, 0, (int)D, (int)H, (int)W, ns, st);
-    if (rc) return rc;
-    rc = launch_fwd<MODE_COMBINE>(cv, x, g_up, out, mask, 1, (int)D, (int)H, (int)W, ns, st);
-    if (rc) return rc;
-    rc = launch_fwd<MODE_COMBINE>(ch, x, g_right, out, mask, 2, (int)D, (int)H, (int)W, ns, st);
-    if (rc) return rc;
-    return launch_fwd<MODE_COMBINE>(ch, x, g_left, out, mask, 3, (int)D, (int)H, (int)W, ns, st);
+    const long long S = D * H * W, HW = H * W, ns = N * C;
+    const float *g[4] = {g_down, g_up, g_right, g_left};
+    VCfg vc;
+    if (!pick_vert_cfg((int)D, &vc))
+        return sga_forward_lines(x, g, out, mask, (int)D, (int)H, (int)W, ns, st);
+    const long long chunk = workspace
+        ? fit_slices([&](long long n) { return fwd_ws(n, S, HW).total; }, workspace_bytes, ns) : 0;
+    if (chunk < 1) return GANET_EWORKSPACE;
+    char *ws = (char *)workspace;
+    const int iD = (int)D, iH = (int)H, iW = (int)W;
+    for (long long s0 = 0; s0 < ns; s0 += chunk) {
+        const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
+        const FwdWs w = fwd_ws(n, S, HW);
+        float *xT = (float *)(ws + w.xT), *outT = (float *)(ws + w.outT);
+        uint8_t *maskT = (uint8_t *)(ws + w.maskT);
+        float *gT2 = (float *)(ws + w.gT2), *gT3 = (float *)(ws + w.gT3);
+        const float *xs = x + s0 * S;
+        float *os = out + s0 * S;
+        uint8_t *ms = mask + s0 * S;
+        // horizontal scans = vertical scans of the H<->W transposed slices
+        if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
+        if ((rc = launch_transpose<float, false>(g_right + s0 * 5 * HW, gT2, n * 5, iH, iW, st))) return rc;
+        if ((rc = launch_transpose<float, false>(g_left + s0 * 5 * HW, gT3, n * 5, iH, iW, st))) return rc;
+        if ((rc = launch_vert_fwd<VMODE_FIRST>(vc, xT, gT2, outT, maskT, 0, MaskIds{2, 2}, iD, iW, iH, n, st))) return rc;
+        if ((rc = launch_vert_fwd<VMODE_SECOND>(vc, xT, gT3, outT, maskT, 1, MaskIds{2, 3}, iD, iW, iH, n, st))) return rc;
+        if ((rc = launch_transpose<float, false>(outT, os, n * D, iW, iH, st))) return rc;
+        if ((rc = launch_transpose<uint8_t, false>(maskT, ms, n * D, iW, iH, st))) return rc;
+        // vertical scans merge on top; the tie rule keeps the lower direction id
+        if ((rc = launch_vert_fwd<VMODE_COMBINE>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+        if ((rc = launch_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st))) return rc;
+    }
+    return GANET_OK;
 }
 
 GANET_API int ganet_sga_direction(const float *x, const float *g, float *a, int dir, int64_t N,
@@ -466,22 +599,39 @@ GANET_API int ganet_sga_direction(const float *x, const float *g, float *a, int 
     int rc = check_dims(N, C, D, H, W);
     if (rc) return rc;
     Cfg c;
+    VCfg vc;
+    if (dir < 2 && pick_vert_cfg((int)D, &vc))
+        return launch_vert_fwd<VMODE_RAW>(vc, x, g, a, nullptr, dir, MaskIds{0, 0}, (int)D, (int)H,
+                                          (int)W, N * C, (cudaStream_t)stream);
     if (!pick_cfg((int)D, dir < 2, &c)) return GANET_EUNSUPPORTED;
     return launch_fwd<MODE_RAW>(c, x, g, a, nullptr, dir, (int)D, (int)H, (int)W, N * C,
                                 (cudaStream_t)stream);
 }
 
-GANET_API size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H,
-                                                  int64_t W)
+// slow generic backward: `a` scratch only
+static int sga_backward_lines(const float *x, const float *const g[4], const uint8_t *mask,
+                              const float *go, float *gi, float *const gg[4], int32_t *max_idx,
+                              float *a, long long chunk, int D, int H, int W, long long ns,
+                              cudaStream_t st)
 {
-    (void)N; (void)C;
-    return (size_t)(D * H * W) * sizeof(float);
-}
-
-GANET_API size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H,
-                                                   int64_t W)
-{
-    return (size_t)(N * C * D * H * W) * sizeof(float);
+    Cfg cv, ch;
+    if (!pick_cfg(D, true, &cv) || !pick_cfg(D, false, &ch)) return GANET_EUNSUPPORTED;
+    const long long S = (long long)D * H * W, HW = (long long)H * W;
+    static const int order[4] = {3, 0, 1, 2};    // the reference's order (:1040, :1061, :1084, :1106)
+    for (long long s0 = 0; s0 < ns; s0 += chunk) {
+        const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
+        for (int o = 0; o < 4; o++) {
+            const int dir = order[o];
+            const Cfg c = dir < 2 ? cv : ch;
+            int rc = launch_fwd<MODE_RAW>(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, nullptr, dir, D, H, W, n, st);
+            if (rc) return rc;
+            rc = launch_bwd(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, mask + s0 * S, go + s0 * S,
+                            gi + s0 * S, gg[dir] + s0 * 5 * HW,
+                            (max_idx && dir == 2) ? max_idx + s0 * HW : nullptr, dir, o > 0, D, H, W, n, st);
+            if (rc) return rc;
+        }
+    }
+    return GANET_OK;
 }
 
 GANET_API int ganet_sga_backward(const float *x, const float *g_down, const float *g_up,
@@ -497,30 +647,51 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
     int rc = check_dims(N, C, D, H, W);
     if (rc) return rc;
     const long long S = D * H * W, HW = H * W, ns = N * C;
-    const long long fit = (long long)(workspace_bytes / (S * sizeof(float)));
-    if (fit < 1) return GANET_EWORKSPACE;
-    const long long chunk = fit < ns ? fit : ns;
     cudaStream_t st = (cudaStream_t)stream;
-    Cfg cv, ch;
-    if (!pick_cfg((int)D, true, &cv) || !pick_cfg((int)D, false, &ch)) return GANET_EUNSUPPORTED;
     const float *g[4] = {g_down, g_up, g_right, g_left};
     float *gg[4] = {gg_down, gg_up, gg_right, gg_left};
-    static const int order[4] = {3, 0, 1, 2};    // the reference's order (:1040, :1061, :1084, :1106)
-    float *a = (float *)workspace;
+    const int iD = (int)D, iH = (int)H, iW = (int)W;
+    VCfg vc;
+    if (!pick_vert_cfg(iD, &vc)) {
+        const long long fit = (long long)(workspace_bytes / ((size_t)S * sizeof(float)));
+        if (fit < 1) return GANET_EWORKSPACE;
+        return sga_backward_lines(x, g, mask, grad_out, grad_in, gg, max_idx, (float *)workspace,
+                                  fit < ns ? fit : ns, iD, iH, iW, ns, st);
+    }
+    const long long chunk =
+        fit_slices([&](long long n) { return bwd_ws(n, S, HW).total; }, workspace_bytes, ns);
+    if (chunk < 1) return GANET_EWORKSPACE;
+    char *ws = (char *)workspace;
     for (long long s0 = 0; s0 < ns; s0 += chunk) {
         const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
-        for (int o = 0; o < 4; o++) {
-            const int dir = order[o];
-            const Cfg c = dir < 2 ? cv : ch;
-            rc = launch_fwd<MODE_RAW>(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, nullptr, dir, (int)D,
-                                      (int)H, (int)W, n, st);
-            if (rc) return rc;
-            rc = launch_bwd(c, x + s0 * S, g[dir] + s0 * 5 * HW, a, mask + s0 * S,
-                            grad_out + s0 * S, grad_in + s0 * S, gg[dir] + s0 * 5 * HW,
-                            (max_idx && dir == 2) ? max_idx + s0 * HW : nullptr, dir, o > 0,
-                            (int)D, (int)H, (int)W, n, st);
-            if (rc) return rc;
+        const BwdWs w = bwd_ws(n, S, HW);
+        float *a = (float *)(ws + w.a), *xT = (float *)(ws + w.xT), *goT = (float *)(ws + w.goT);
+        float *giT = (float *)(ws + w.giT), *gT = (float *)(ws + w.gT), *ggT = (float *)(ws + w.ggT);
+        uint8_t *maskT = (uint8_t *)(ws + w.maskT);
+        const float *xs = x + s0 * S, *gos = grad_out + s0 * S;
+        const uint8_t *ms = mask + s0 * S;
+        float *gis = grad_in + s0 * S;
+        // vertical directions in place
+        for (int dir = 0; dir < 2; dir++) {
+            if ((rc = launch_vert_fwd<VMODE_RAW>(vc, xs, g[dir] + s0 * 5 * HW, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+            if ((rc = launch_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, a, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
         }
+        // horizontal directions on the transposed slices
+        if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
+        if ((rc = launch_transpose<float, false>(gos, goT, n * D, iH, iW, st))) return rc;
+        if ((rc = launch_transpose<uint8_t, false>(ms, maskT, n * D, iH, iW, st))) return rc;
+        for (int dir = 2; dir < 4; dir++) {
+            if ((rc = launch_transpose<float, false>(g[dir] + s0 * 5 * HW, gT, n * 5, iH, iW, st))) return rc;
+            if ((rc = launch_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
+            if (max_idx && dir == 2) {
+                dim3 grid((unsigned)((HW + 255) / 256), (unsigned)n);
+                max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(a, max_idx + s0 * HW, iD, iH, iW);
+                GANET_RETURN_IF_LAUNCH_FAILED();
+            }
+            if ((rc = launch_vert_bwd(vc, xT, gT, a, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
+            if ((rc = launch_transpose<float, false>(ggT, gg[dir] + s0 * 5 * HW, n * 5, iW, iH, st))) return rc;
+        }
+        if ((rc = launch_transpose<float, true>(giT, gis, n * D, iW, iH, st))) return rc;   // gi += giT^T
     }
     return GANET_OK;
 }

@@ -1,0 +1,72 @@
+// Plane transposes (H <-> W) used to run the horizontal SGA scans as coalesced
+// vertical scans: src is `planes` matrices of R rows x Cc columns, dst the same
+// planes with Cc rows x R columns.  32x32 tiles through padded shared memory, both
+// sides read/written in full rows.  ACC: dst += transpose(src) (fp32 only).
+#pragma once
+#include "common.cuh"
+
+namespace ganet {
+
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(256)
+transpose_planes_kernel(const T *__restrict__ src, T *dst, int R, int Cc)
+{
+    __shared__ T tile[32][33];
+    const long long plane = blockIdx.z;
+    const T *sp = src + plane * (long long)R * Cc;
+    T *dp = dst + plane * (long long)R * Cc;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int r = r0 + ty + k, c = c0 + tx;
+        if (r < R && c < Cc) tile[ty + k][tx] = sp[(long long)r * Cc + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int c = c0 + ty + k, r = r0 + tx;                // dst row = c, dst col = r
+        if (r < R && c < Cc) {
+            const long long e = (long long)c * R + r;
+            if (ACC) dp[e] = dp[e] + tile[tx][ty + k];
+            else dp[e] = tile[tx][ty + k];
+        }
+    }
+}
+
+template <typename T, bool ACC>
+static int launch_transpose(const T *src, T *dst, long long planes, int R, int Cc, cudaStream_t st)
+{
+    if (planes <= 0) return GANET_OK;
+    const long long zmax = 65535;
+    for (long long z0 = 0; z0 < planes; z0 += zmax) {         // gridDim.z limit
+        const long long nz = planes - z0 < zmax ? planes - z0 : zmax;
+        dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)nz);
+        transpose_planes_kernel<T, ACC><<<grid, 256, 0, st>>>(src + z0 * (long long)R * Cc,
+                                                              dst + z0 * (long long)R * Cc, R, Cc);
+    }
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+// first arg-max over depth per pixel of a TRANSPOSED aggregate aT[D][W][H], written in
+// the standard layout idx[H][W] (MaxDepth, GANet_kernel.cu:50-64)
+__global__ void __launch_bounds__(256)
+max_depth_from_transposed_kernel(const float *__restrict__ aT, int32_t *__restrict__ idx, int D,
+                                 int H, int W)
+{
+    const long long s = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;      // q = w * H + h
+    if (q >= H * W) return;
+    const float *ap = aT + s * (long long)D * H * W + q;
+    float best = ld_nc(ap);
+    int k = 0;
+    for (int d = 1; d < D; d++) {
+        const float v = ld_nc(ap + (long long)d * H * W);
+        if (best < v) { best = v; k = d; }
+    }
+    const int w = q / H, h = q - w * H;
+    idx[s * (long long)H * W + (long long)h * W + w] = k;
+}
+
+}  // namespace ganet

@@ -19,10 +19,18 @@ def _dims5(x):
 
 
 def _workspace_budget():
-    return int(os.environ.get("GANET_B200_WORKSPACE_BYTES", str(6 << 30)))
+    return int(os.environ.get("GANET_B200_WORKSPACE_BYTES", str(8 << 30)))
 
 
-def sga_forward(x, g0, g1, g2, g3):
+def _workspace(x, ws_min, ws_best, workspace_bytes):
+    """Scratch for one call: as much of `best` as the budget allows, never below `min`
+    (the native side walks the (n,c) slices in chunks that fit)."""
+    budget = _workspace_budget() if workspace_bytes is None else int(workspace_bytes)
+    nbytes = int(min(ws_best, max(ws_min, budget)))
+    return torch.empty(nbytes, dtype=torch.uint8, device=x.device), nbytes
+
+
+def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None):
     """-> out (N,C,D,H,W) f32, mask (N,C,D,H,W) u8"""
     N, C, D, H, W = x.shape
     for g in (g0, g1, g2, g3):
@@ -31,8 +39,13 @@ def sga_forward(x, g0, g1, g2, g3):
     with torch.cuda.device_of(x):
         out = torch.empty_like(x)
         mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-        check(_lib.lib().ganet_sga_forward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(out),
-                                           ptr(mask, torch.uint8), *_dims5(x), stream()))
+        L = _lib.lib()
+        dims = _dims5(x)
+        ws, ws_bytes = _workspace(x, L.ganet_sga_forward_workspace_min(*dims),
+                                  L.ganet_sga_forward_workspace_best(*dims), workspace_bytes)
+        check(L.ganet_sga_forward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(out),
+                                  ptr(mask, torch.uint8), ptr(ws, torch.uint8), _lib._sz(ws_bytes),
+                                  *dims, stream()))
     return out, mask
 
 
@@ -54,11 +67,8 @@ def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspac
         gg = [torch.empty_like(g0) for _ in range(4)]
         idx = torch.empty((N, C, H, W), dtype=torch.int32, device=x.device) if want_max_idx else None
         dims = _dims5(x)
-        ws_min = L.ganet_sga_backward_workspace_min(*dims)
-        ws_best = L.ganet_sga_backward_workspace_best(*dims)
-        budget = _workspace_budget() if workspace_bytes is None else int(workspace_bytes)
-        ws_bytes = min(ws_best, max(ws_min, budget // ws_min * ws_min))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        ws, ws_bytes = _workspace(x, L.ganet_sga_backward_workspace_min(*dims),
+                                  L.ganet_sga_backward_workspace_best(*dims), workspace_bytes)
         check(L.ganet_sga_backward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3),
                                    ptr(mask, torch.uint8), ptr(grad_out), ptr(gi), ptr(gg[0]),
                                    ptr(gg[1]), ptr(gg[2]), ptr(gg[3]),

@@ -66,15 +66,20 @@ const char *ganet_error_string(int code);
  *       L1-normalised them over dim 2 (models/GANet_deep.py:265-268)
  *   mask   : (N, C, D, H, W) uint8, winning direction 0=down 1=up 2=right
  *       3=left, ties keep the lower id (GANet_kernel.cu:23-36)
+ *   workspace : device scratch (transposed copies for the horizontal scans),
+ *       >= ganet_sga_forward_workspace_min bytes; the (n,c) slices are processed
+ *       in chunks that fit, so any size between _min and _best works
  * Values of `out` and `mask` are bit-identical to the reference CUDA build.
  */
 int ganet_sga_forward(const float *x, const float *g_down, const float *g_up,
                       const float *g_right, const float *g_left, float *out,
-                      uint8_t *mask, int64_t N, int64_t C, int64_t D, int64_t H,
-                      int64_t W, ganet_stream_t stream);
+                      uint8_t *mask, void *workspace, size_t workspace_bytes, int64_t N,
+                      int64_t C, int64_t D, int64_t H, int64_t W, ganet_stream_t stream);
 
-/* Bytes of scratch ganet_sga_backward needs at least (one (n,c) slice of
- * recomputed aggregate) and the size at which it runs fastest (all slices). */
+/* Bytes of scratch the SGA calls need at least (one (n,c) slice in flight) and
+ * the size at which they run all slices in one chunk. */
+size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
+size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 

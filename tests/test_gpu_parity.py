@@ -128,6 +128,8 @@ def test_sga_backward_workspace_chunking_is_invisible(ops):
     b = ops.sga_backward(xt, *gt, mask, got, workspace_bytes=1 << 30)
     assert torch.equal(a[0], b[0])
     assert all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+    o1, m1 = ops.sga_forward(xt, *gt, workspace_bytes=1)
+    assert torch.equal(o1, out) and torch.equal(m1, mask)
 
 
 def test_sga_against_golden_vectors(ops):

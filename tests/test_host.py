@@ -56,13 +56,21 @@ def test_argument_validation_without_gpu(native_so):
     from ganet_b200 import _lib
     L = _lib.lib()
     i64 = ctypes.c_int64
-    assert L.ganet_sga_forward(None, None, None, None, None, None, None,
+    sz = ctypes.c_size_t
+    assert L.ganet_sga_forward(None, None, None, None, None, None, None, None, sz(0),
                                i64(1), i64(1), i64(1), i64(1), i64(1), None) == -1
     dummy = ctypes.c_void_p(16)
-    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy,
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, sz(1 << 20),
                                i64(1), i64(1), i64(1000), i64(1), i64(1), None) == -2   # D > 768
-    assert L.ganet_sga_backward_workspace_min(i64(2), i64(3), i64(4), i64(5), i64(6)) == 4 * 5 * 6 * 4
-    assert L.ganet_sga_backward_workspace_best(i64(2), i64(3), i64(4), i64(5), i64(6)) == 6 * 120 * 4
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, sz(16),
+                               i64(1), i64(1), i64(8), i64(4), i64(4), None) == -3     # workspace too small
+    dims = (i64(2), i64(3), i64(4), i64(5), i64(6))
+    S, HW = 4 * 5 * 6, 5 * 6
+    fmin, fbest = L.ganet_sga_forward_workspace_min(*dims), L.ganet_sga_forward_workspace_best(*dims)
+    bmin, bbest = L.ganet_sga_backward_workspace_min(*dims), L.ganet_sga_backward_workspace_best(*dims)
+    assert 9 * S + 40 * HW <= fmin <= 9 * S + 40 * HW + 5 * 256      # xT, outT (f32) + maskT (u8) + 2 guidance
+    assert 17 * S + 40 * HW <= bmin <= 17 * S + 40 * HW + 7 * 256    # a, xT, goT, giT + maskT + g, gg
+    assert fmin < fbest <= 6 * fmin and bmin < bbest <= 6 * bmin
     d2 = ctypes.c_void_p(32)
     assert L.ganet_lga_forward(dummy, dummy, d2, i64(1), i64(1), i64(1), i64(1), 9, None) == -2
     assert L.ganet_lga_forward(dummy, dummy, dummy, i64(1), i64(1), i64(1), i64(1), 2, None) == -1   # y aliases x
