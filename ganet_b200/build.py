@@ -36,7 +36,9 @@ def _nvcc():
 
 def _deps(src):
     yield os.path.join(CSRC, src)
-    yield os.path.join(CSRC, "common.cuh")
+    for f in sorted(os.listdir(CSRC)):          # every header: cheap, and never stale
+        if f.endswith((".cuh", ".h")):
+            yield os.path.join(CSRC, f)
     yield os.path.join(HERE, "..", "include", "ganet_b200.h")
 
 

@@ -75,4 +75,16 @@ __device__ __forceinline__ float from_next_chunk(float v)
 
 __device__ __forceinline__ float ld_nc(const float *p) { return __ldg(p); }
 
+// address = 64-bit row base + 32-bit byte offset in ONE instruction (IMAD.WIDE.U32).
+// Left to itself nvcc rebuilds base + (int64)(off + pix) * 4 with four integer
+// instructions per access, which made the scan kernels issue-bound.
+typedef unsigned long long addr_t;
+template <typename T>
+__device__ __forceinline__ T *at(addr_t base, unsigned off_bytes)
+{
+    addr_t a;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(a) : "r"(off_bytes), "l"(base));
+    return reinterpret_cast<T *>(a);
+}
+
 }  // namespace ganet

@@ -26,6 +26,7 @@
 // K is always even, so the parity of d = K*j + i is the parity of the unrolled
 // index i and the choice is made at compile time.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sga_step.cuh"
@@ -401,7 +402,7 @@ static int launch_bwd(Cfg c, const float *x, const float *g, const float *a, con
 }
 
 // ---- vertical (coalesced) kernels: (K, MAXW) instantiations -------------------------
-#define GANET_VERT_CFGS(X) X(2, 16) X(4, 16) X(6, 16) X(12, 16) X(24, 12)
+#define GANET_VERT_CFGS(X) X(2, 16) X(4, 16) X(6, 16) X(6, 32) X(12, 16) X(24, 12)
 
 struct VCfg { int K, NW; };
 
@@ -409,6 +410,11 @@ static bool pick_vert_cfg(int D, VCfg *out)
 {
     static const int ks[] = {2, 4, 6, 12, 24};
     static const int mw[] = {16, 16, 16, 16, 12};
+    if (const char *env = getenv("GANET_VERT_K")) {            // tuning aid
+        const int k = atoi(env);
+        for (int i = 0; i < 5; i++)
+            if (ks[i] == k && (D + k - 1) / k <= (k == 6 ? 32 : mw[i])) { out->K = k; out->NW = (D + k - 1) / k; return true; }
+    }
     for (int i = 0; i < 5; i++) {
         const int nw = (D + ks[i] - 1) / ks[i];
         if (nw <= mw[i]) { out->K = ks[i]; out->NW = nw; return true; }
@@ -426,10 +432,15 @@ static int launch_vert_fwd(VCfg c, const float *x, const float *g, float *out, u
     if (blocks <= 0) return GANET_OK;
     if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
     const size_t smem = (size_t)2 * 3 * c.NW * 32 * sizeof(float);
+    const bool full = c.K * c.NW == D;
 #define X(K_, W_)                                                                            \
-    if (c.K == K_) {                                                                         \
-        sga_vert_fwd_kernel<K_, W_, MODE><<<(unsigned)blocks, c.NW * 32, smem, st>>>(        \
-            x, g, out, mask, dir, ids, D, H, W, strips);                                     \
+    if (c.K == K_ && c.NW <= W_) {                                                           \
+        if (full)                                                                            \
+            sga_vert_fwd_kernel<K_, W_, MODE, true><<<(unsigned)blocks, c.NW * 32, smem, st>>>( \
+                x, g, out, mask, dir, ids, D, H, W, strips);                                 \
+        else                                                                                 \
+            sga_vert_fwd_kernel<K_, W_, MODE, false><<<(unsigned)blocks, c.NW * 32, smem, st>>>( \
+                x, g, out, mask, dir, ids, D, H, W, strips);                                 \
     } else
     GANET_VERT_CFGS(X) { return GANET_EUNSUPPORTED; }
 #undef X
@@ -447,10 +458,21 @@ static int launch_vert_bwd(VCfg c, const float *x, const float *g, const float *
     if (blocks <= 0) return GANET_OK;
     if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
     const size_t smem = (size_t)2 * NBW * c.NW * 32 * sizeof(float);
+    const bool full = c.K * c.NW == D;
 #define X(K_, W_)                                                                            \
-    if (c.K == K_) {                                                                         \
-        sga_vert_bwd_kernel<K_, W_><<<(unsigned)blocks, c.NW * 32, smem, st>>>(              \
-            x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W, strips);           \
+    if (c.K == K_ && c.NW <= W_) {                                                           \
+        if (smem > 48 * 1024) {                                                              \
+            cudaFuncSetAttribute(sga_vert_bwd_kernel<K_, W_, true>,                          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            cudaFuncSetAttribute(sga_vert_bwd_kernel<K_, W_, false>,                         \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        }                                                                                    \
+        if (full)                                                                            \
+            sga_vert_bwd_kernel<K_, W_, true><<<(unsigned)blocks, c.NW * 32, smem, st>>>(    \
+                x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W, strips);       \
+        else                                                                                 \
+            sga_vert_bwd_kernel<K_, W_, false><<<(unsigned)blocks, c.NW * 32, smem, st>>>(   \
+                x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W, strips);       \
     } else
     GANET_VERT_CFGS(X) { return GANET_EUNSUPPORTED; }
 #undef X

@@ -36,11 +36,15 @@ struct MaskIds { int first, mine; };   // direction ids written to the mask
 // are separate because the horizontal scans run as vertical scans on transposed data.
 // smem: float[2][3][NW][32]
 // ---------------------------------------------------------------------------
-template <int K, int MAXW, int MODE>
+template <int K, int MAXW, int MODE, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32)
 sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, float *out,
                     uint8_t *mask, int dir, MaskIds ids, int D, int H, int W, int strips)
 {
+    // FULL: NW * K == D, so no thread owns a depth >= D and every depth predicate
+    // disappears.  Addresses are walked as pointers (plane stride HW per depth, row
+    // stride ps per scan step): rebuilding base + (offset + pixel) * 4 for every
+    // access cost 6 integer instructions per load in the first version of this kernel.
     static_assert(K % 2 == 0, "depth parity must be a compile-time property");
     extern __shared__ float ex[];
     const int lane = threadIdx.x & 31, j = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -49,36 +53,45 @@ sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
     const int wcol = strip * 32 + lane;
     const bool wok = wcol < W;
     const int wc = wok ? wcol : W - 1;
-    const int HW = H * W;
+    const long long HW = (long long)H * W;
     const long long S = (long long)D * HW;
-    const float *xs = x + s * S;
-    const float *gs = g + s * 5ll * HW;
-    float *os = out + s * S;
-    uint8_t *ms = (MODE == VMODE_RAW || MODE == VMODE_FIRST) ? nullptr : mask + s * S;
-
     const int d0 = K * j;
-    int off[K];
-#pragma unroll
-    for (int i = 0; i < K; i++) off[i] = min(d0 + i, D - 1) * HW;
+    const int dfirst = FULL ? d0 : min(d0, D - 1);
+    const long long ps = (dir == 0) ? W : -W;
+    const long long e0 = s * S + dfirst * HW + ((dir == 0) ? wc : (long long)(H - 1) * W + wc);
+    // row base addresses (depth d0, current scan row) as integers, walked by `ps` per row
+    addr_t xrow = (addr_t)(x + e0);
+    addr_t orow = (addr_t)(out + e0);
+    addr_t mrow = (MODE == VMODE_RAW || MODE == VMODE_FIRST) ? 0 : (addr_t)(mask + e0);
+    addr_t grow = (addr_t)(g + s * 5 * HW + ((dir == 0) ? wc : (long long)(H - 1) * W + wc));
+    const long long psb = ps * 4;                 // row step in bytes (fp32 tensors)
 
-    int p = (dir == 0) ? wc : (H - 1) * W + wc;
-    const int ps = (dir == 0) ? W : -W;
     const int plane = NW * 32;               // one exchange array
+    unsigned offb[K];                        // byte offset of depth d0+i within the row base
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        offb[i] = (unsigned)(i * (int)HW) * 4u;
+        asm volatile("" : "+r"(offb[i]));    // per-thread register, not re-derived each use
+    }
     float P[K], xc[K], w[5];
 #pragma unroll
-    for (int i = 0; i < K; i++) { xc[i] = ld_nc(xs + off[i] + p); P[i] = 0.f; }
+    for (int i = 0; i < K; i++) {
+        xc[i] = (FULL || d0 + i < D) ? ld_nc(at<const float>(xrow, offb[i])) : 0.f;
+        P[i] = 0.f;
+    }
 #pragma unroll
-    for (int k = 0; k < 5; k++) w[k] = ld_nc(gs + k * HW + p);
+    for (int k = 0; k < 5; k++) w[k] = ld_nc(at<const float>(grow, (unsigned)(k * (int)HW) * 4u));
 
     for (int t = 0; t < H; t++) {
-        const int pn = p + ps;
         float xn[K], wn[5], oc[K];
         uint8_t mc[K];
         if (t + 1 < H) {
+            const addr_t xnext = xrow + psb, gnext = grow + psb;
 #pragma unroll
-            for (int i = 0; i < K; i++) xn[i] = ld_nc(xs + off[i] + pn);
+            for (int i = 0; i < K; i++)
+                xn[i] = (FULL || d0 + i < D) ? ld_nc(at<const float>(xnext, offb[i])) : 0.f;
 #pragma unroll
-            for (int k = 0; k < 5; k++) wn[k] = ld_nc(gs + k * HW + pn);
+            for (int k = 0; k < 5; k++) wn[k] = ld_nc(at<const float>(gnext, (unsigned)(k * (int)HW) * 4u));
         } else {
 #pragma unroll
             for (int i = 0; i < K; i++) xn[i] = 0.f;
@@ -87,11 +100,12 @@ sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
         }
         if (MODE == VMODE_SECOND || MODE == VMODE_COMBINE) {
 #pragma unroll
-            for (int i = 0; i < K; i++) oc[i] = os[off[i] + p];
+            for (int i = 0; i < K; i++) oc[i] = (FULL || d0 + i < D) ? *at<const float>(orow, offb[i]) : 0.f;
         }
         if (MODE == VMODE_COMBINE) {
 #pragma unroll
-            for (int i = 0; i < K; i++) mc[i] = ms[off[i] + p];
+            for (int i = 0; i < K; i++)
+                mc[i] = (FULL || d0 + i < D) ? *at<const uint8_t>(mrow, offb[i] >> 2) : (uint8_t)0;
         }
 
         float A[K];
@@ -101,30 +115,33 @@ sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
             const float *eb = ex + ((t - 1) & 1) * 3 * plane;
             const float up = (j > 0) ? eb[plane + (j - 1) * 32 + lane] : 0.f;       // P[d0-1]
             const float dn = (j + 1 < NW) ? eb[(j + 1) * 32 + lane] : 0.f;          // P[d0+K]
-            float pmax = eb[2 * plane + lane];
-            for (int jj = 1; jj < NW; jj++) pmax = fmaxf(pmax, eb[2 * plane + jj * 32 + lane]);
-            sga_next_step<K>(P, xc, w, up, dn, pmax, d0, D, A);
+            const float *mx = eb + 2 * plane + lane;
+            float pmax = mx[0];
+            for (int jj = 1; jj < NW; jj++) pmax = fmaxf(pmax, mx[jj * 32]);
+            sga_next_step<K, FULL>(P, xc, w, up, dn, pmax, d0, D, A);
         }
         {
-            float *wb = ex + (t & 1) * 3 * plane;
-            wb[j * 32 + lane] = A[0];
-            wb[plane + j * 32 + lane] = A[K - 1];
-            wb[2 * plane + j * 32 + lane] = chunk_max<K>(A, d0, D);
+            float *wb = ex + (t & 1) * 3 * plane + j * 32 + lane;
+            wb[0] = A[0];
+            wb[plane] = A[K - 1];
+            wb[2 * plane] = FULL ? chunk_max<K>(A, 0, K) : chunk_max<K>(A, d0, D);
         }
         if (wok) {
 #pragma unroll
             for (int i = 0; i < K; i++) {
-                if (d0 + i < D) {
-                    const int e = off[i] + p;
+                if (FULL || d0 + i < D) {
                     if (MODE == VMODE_FIRST || MODE == VMODE_RAW) {
-                        os[e] = A[i];
+                        *at<float>(orow, offb[i]) = A[i];
                     } else if (MODE == VMODE_SECOND) {
                         const bool m = oc[i] < A[i];
-                        if (m) os[e] = A[i];
-                        ms[e] = m ? (uint8_t)ids.mine : (uint8_t)ids.first;
+                        if (m) *at<float>(orow, offb[i]) = A[i];
+                        *at<uint8_t>(mrow, offb[i] >> 2) = m ? (uint8_t)ids.mine : (uint8_t)ids.first;
                     } else {
                         const bool m = oc[i] < A[i] || (oc[i] == A[i] && ids.mine < (int)mc[i]);
-                        if (m) { os[e] = A[i]; ms[e] = (uint8_t)ids.mine; }
+                        if (m) {
+                            *at<float>(orow, offb[i]) = A[i];
+                            *at<uint8_t>(mrow, offb[i] >> 2) = (uint8_t)ids.mine;
+                        }
                     }
                 }
             }
@@ -134,7 +151,8 @@ sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
         for (int i = 0; i < K; i++) { P[i] = A[i]; xc[i] = xn[i]; }
 #pragma unroll
         for (int k = 0; k < 5; k++) w[k] = wn[k];
-        p = pn;
+        xrow += psb; orow += psb; grow += psb;
+        if (MODE == VMODE_SECOND || MODE == VMODE_COMBINE) mrow += ps;      // bytes: u8 tensor
     }
 }
 
@@ -145,7 +163,7 @@ sga_vert_fwd_kernel(const float *__restrict__ x, const float *__restrict__ g, fl
 // ---------------------------------------------------------------------------
 enum { BX_TLO = 0, BX_THI, BX_ST, BX_S0, BX_S1, BX_S2, BX_S3, BX_AMAX, BX_AIDX, NBW };
 
-template <int K, int MAXW>
+template <int K, int MAXW, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32)
 sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
                     const float *__restrict__ a, const uint8_t *__restrict__ mask,
@@ -159,68 +177,75 @@ sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
     const int wcol = strip * 32 + lane;
     const bool wok = wcol < W;
     const int wc = wok ? wcol : W - 1;
-    const int HW = H * W;
+    const long long HW = (long long)H * W;
     const long long S = (long long)D * HW;
-    const float *xs = x + s * S;
-    const float *as = a + s * S;
-    const float *gos = go + s * S;
-    const uint8_t *ms = mask + s * S;
-    float *gis = gi + s * S;
-    const float *gs = g + s * 5ll * HW;
-    float *ggs = gg + s * 5ll * HW;
-
     const int d0 = K * j;
-    int off[K];
+    const int dfirst = FULL ? d0 : min(d0, D - 1);
+    const long long ps = (dir == 0) ? W : -W;                 // forward scan step
+    // last scan position of this column
+    const long long pix = ((dir == 0) ? wc : (long long)(H - 1) * W + wc) + (H - 1) * ps;
+    const long long e0 = s * S + dfirst * HW + pix;
+    const long long psb = ps * 4;
+    addr_t xrow = (addr_t)(x + e0);
+    addr_t arow = (addr_t)(a + e0 - ps);                      // aggregate at scan position t-1
+    addr_t gorow = (addr_t)(go + e0);
+    addr_t mrow = (addr_t)(mask + e0);
+    addr_t girow = (addr_t)(gi + e0);
+    addr_t grow = (addr_t)(g + s * 5 * HW + pix);
+    float *ggrow = gg + s * 5 * HW + pix;
+    // neighbours across the chunk edges come straight from global memory
+    addr_t auprow = (addr_t)(a + e0 - ps + ((d0 >= 1) ? -HW : 0));                        // depth d0-1
+    addr_t adnrow = (addr_t)(a + e0 - ps + (long long)(min(d0 + K, D - 1) - dfirst) * HW);   // depth d0+K
+    unsigned offb[K];
 #pragma unroll
-    for (int i = 0; i < K; i++) off[i] = min(d0 + i, D - 1) * HW;
-    const int off_m1 = max(d0 - 1, 0) * HW;            // depth d0-1 (edge of the previous chunk)
-    const int off_pK = min(d0 + K, D - 1) * HW;        // depth d0+K (edge of the next chunk)
+    for (int i = 0; i < K; i++) {
+        offb[i] = (unsigned)(i * (int)HW) * 4u;
+        asm volatile("" : "+r"(offb[i]));
+    }
 
-    const int ps = (dir == 0) ? W : -W;                // forward scan step
-    int p = ((dir == 0) ? wc : (H - 1) * W + wc) + (H - 1) * ps;   // last scan position
     const int plane = NW * 32;
     const int bufsz = NBW * plane;
-
     float Tn[K], wnx[5];
 #pragma unroll
     for (int i = 0; i < K; i++) Tn[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < 5; k++) wnx[k] = 0.f;
-    int p_next = p;                                    // pixel of scan position t+1
+    float *gg_next = ggrow;                                   // guidance-gradient pixel of position t+1
 
     for (int t = H - 1; t >= 0; t--) {
-        const int pq = p - ps;                         // scan position t-1
         float xv[K], t0[K], ap[K], w[5], gold[K];
         float aup = 0.f, adn = 0.f;
+        {
 #pragma unroll
-        for (int i = 0; i < K; i++) {
-            const int e = off[i] + p;
-            xv[i] = ld_nc(xs + e);
-            const float gv = ld_nc(gos + e);
-            const uint8_t mv = ms[e];
-            t0[i] = (d0 + i < D && mv == mask_id) ? gv : 0.f;        // get_temp_grad :38-48
-            ap[i] = (t >= 1) ? ld_nc(as + off[i] + pq) : 0.f;
-            gold[i] = accumulate ? gis[e] : 0.f;
-        }
-        if (t >= 1) {
-            aup = ld_nc(as + off_m1 + pq);             // A[d0-1, t-1]
-            adn = ld_nc(as + off_pK + pq);             // A[d0+K, t-1]
-        }
+            for (int i = 0; i < K; i++) {
+                const bool ok = FULL || d0 + i < D;
+                xv[i] = ok ? ld_nc(at<const float>(xrow, offb[i])) : 0.f;
+                const float gv = ok ? ld_nc(at<const float>(gorow, offb[i])) : 0.f;
+                const uint8_t mv = ok ? *at<const uint8_t>(mrow, offb[i] >> 2) : (uint8_t)255;
+                t0[i] = (mv == mask_id) ? gv : 0.f;                       // get_temp_grad :38-48
+                ap[i] = (ok && t >= 1) ? ld_nc(at<const float>(arow, offb[i])) : 0.f;
+                gold[i] = (ok && accumulate) ? *at<const float>(girow, offb[i]) : 0.f;
+            }
+            if (t >= 1) {
+                aup = ld_nc((const float *)auprow);                       // A[d0-1, t-1]
+                adn = ld_nc((const float *)adnrow);                       // A[d0+K, t-1]
+            }
 #pragma unroll
-        for (int k = 0; k < 5; k++) w[k] = ld_nc(gs + k * HW + p);
+            for (int k = 0; k < 5; k++) w[k] = ld_nc(at<const float>(grow, (unsigned)(k * (int)HW) * 4u));
+        }
 
         float tc[K];
         if (t + 1 < H) {
             // everything the previous iteration (scan position t+1) published
-            const float *eb = ex + ((t + 1) & 1) * bufsz;
-            const float up = (j > 0) ? eb[BX_THI * plane + (j - 1) * 32 + lane] : 0.f;
-            const float dn = (j + 1 < NW) ? eb[BX_TLO * plane + (j + 1) * 32 + lane] : 0.f;
+            const float *eb = ex + ((t + 1) & 1) * bufsz + lane;
+            const float up = (j > 0) ? eb[BX_THI * plane + (j - 1) * 32] : 0.f;
+            const float dn = (j + 1 < NW) ? eb[BX_TLO * plane + (j + 1) * 32] : 0.f;
             float sum_tn = 0.f, amax = -INFINITY;
             int idx_cur = 0x7fffffff;
             for (int jj = 0; jj < NW; jj++) {
-                sum_tn += eb[BX_ST * plane + jj * 32 + lane];
-                const float v = eb[BX_AMAX * plane + jj * 32 + lane];
-                const int vi = __float_as_int(eb[BX_AIDX * plane + jj * 32 + lane]);
+                sum_tn += eb[BX_ST * plane + jj * 32];
+                const float v = eb[BX_AMAX * plane + jj * 32];
+                const int vi = __float_as_int(eb[BX_AIDX * plane + jj * 32]);
                 if (v > amax) { amax = v; idx_cur = vi; }          // strict >: first maximum
             }
             // guidance gradients of scan position t+1 are complete now: one warp per weight
@@ -230,9 +255,9 @@ sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
                     tot = sum_tn * amax;                           // (:265-272)
                 } else {
                     tot = 0.f;
-                    for (int jj = 0; jj < NW; jj++) tot += eb[(BX_S0 + k) * plane + jj * 32 + lane];
+                    for (int jj = 0; jj < NW; jj++) tot += eb[(BX_S0 + k) * plane + jj * 32];
                 }
-                if (wok) ggs[k * HW + p_next] = tot;
+                if (wok) gg_next[k * (int)HW] = tot;
             }
             const float inj = sum_tn * wnx[4];
 #pragma unroll
@@ -245,7 +270,7 @@ sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
                 if (d + 1 < D) v += tp * wnx[2];
                 if (d >= 1) v += tm * wnx[3];
                 if (d == idx_cur) v += inj;
-                tc[i] = (d < D) ? v : 0.f;
+                tc[i] = (FULL || d < D) ? v : 0.f;
             }
         } else {
 #pragma unroll
@@ -256,11 +281,11 @@ sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
 #pragma unroll
             for (int i = 0; i < K; i++) {
                 const int d = d0 + i;
-                if (d < D) {
+                if (FULL || d < D) {
                     float v = tc[i] * w[0];
                     if (d == 0) v += tc[i] * w[2];
                     if (d == D - 1) v += tc[i] * w[3];
-                    gis[off[i] + p] = gold[i] + v;
+                    *at<float>(girow, offb[i]) = gold[i] + v;
                 }
             }
         }
@@ -279,38 +304,39 @@ sga_vert_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
                 s1 += tc[i] * ap[i];
                 s2 += tc[i] * ((d >= 1) ? am : xv[i]);
                 s3 += tc[i] * ((d + 1 < D) ? apn : xv[i]);
-                if (d < D && ap[i] > best) { best = ap[i]; bi = d; }
+                if ((FULL || d < D) && ap[i] > best) { best = ap[i]; bi = d; }
             }
         }
         {
-            float *wb = ex + (t & 1) * bufsz;
-            const int o = j * 32 + lane;
-            wb[BX_TLO * plane + o] = tc[0];
-            wb[BX_THI * plane + o] = tc[K - 1];
-            wb[BX_ST * plane + o] = st;
-            wb[BX_S0 * plane + o] = s0;
-            wb[BX_S1 * plane + o] = s1;
-            wb[BX_S2 * plane + o] = s2;
-            wb[BX_S3 * plane + o] = s3;
-            wb[BX_AMAX * plane + o] = best;
-            wb[BX_AIDX * plane + o] = __int_as_float(bi);
+            float *wb = ex + (t & 1) * bufsz + j * 32 + lane;
+            wb[BX_TLO * plane] = tc[0];
+            wb[BX_THI * plane] = tc[K - 1];
+            wb[BX_ST * plane] = st;
+            wb[BX_S0 * plane] = s0;
+            wb[BX_S1 * plane] = s1;
+            wb[BX_S2 * plane] = s2;
+            wb[BX_S3 * plane] = s3;
+            wb[BX_AMAX * plane] = best;
+            wb[BX_AIDX * plane] = __int_as_float(bi);
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < K; i++) Tn[i] = tc[i];
 #pragma unroll
         for (int k = 0; k < 5; k++) wnx[k] = w[k];
-        p_next = p;
-        p = pq;
+        gg_next = ggrow;
+        xrow -= psb; arow -= psb; gorow -= psb; girow -= psb; grow -= psb; auprow -= psb; adnrow -= psb;
+        mrow -= ps;                                            // bytes: u8 tensor
+        ggrow -= ps;
     }
     // scan position 0: only w0 receives a gradient (Appendix A.3 quirk)
     {
-        const float *eb = ex + 0 * bufsz;
+        const float *eb = ex + lane;
         for (int k = j; k < 5; k += NW) {
             float tot = 0.f;
             if (k == 0)
-                for (int jj = 0; jj < NW; jj++) tot += eb[BX_S0 * plane + jj * 32 + lane];
-            if (wok) ggs[k * HW + p_next] = tot;
+                for (int jj = 0; jj < NW; jj++) tot += eb[BX_S0 * plane + jj * 32];
+            if (wok) gg_next[k * (int)HW] = tot;
         }
     }
 }

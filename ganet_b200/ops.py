@@ -18,14 +18,19 @@ def _dims5(x):
     return [_i64(int(v)) for v in x.shape]
 
 
-def _workspace_budget():
-    return int(os.environ.get("GANET_B200_WORKSPACE_BYTES", str(8 << 30)))
+def _workspace_budget(device=None):
+    """Scratch budget per call: GANET_B200_WORKSPACE_BYTES, else a quarter of the device
+    memory (45 GB on a 180 GB B200) -- enough for a 920M-voxel sample in one chunk."""
+    env = os.environ.get("GANET_B200_WORKSPACE_BYTES")
+    if env:
+        return int(env)
+    return torch.cuda.get_device_properties(device).total_memory // 4
 
 
 def _workspace(x, ws_min, ws_best, workspace_bytes):
     """Scratch for one call: as much of `best` as the budget allows, never below `min`
     (the native side walks the (n,c) slices in chunks that fit)."""
-    budget = _workspace_budget() if workspace_bytes is None else int(workspace_bytes)
+    budget = _workspace_budget(x.device) if workspace_bytes is None else int(workspace_bytes)
     nbytes = int(min(ws_best, max(ws_min, budget)))
     return torch.empty(nbytes, dtype=torch.uint8, device=x.device), nbytes
 
@@ -36,6 +41,8 @@ def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None):
     for g in (g0, g1, g2, g3):
         if tuple(g.shape) != (N, C, 5, H, W):
             raise ValueError("guidance must be (N,C,5,H,W), got %s" % (tuple(g.shape),))
+    for t in (x, g0, g1, g2, g3):
+        ptr(t)                      # device / dtype / layout checks before any allocation
     with torch.cuda.device_of(x):
         out = torch.empty_like(x)
         mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
@@ -62,6 +69,8 @@ def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspac
     """-> grad_in, (gg0, gg1, gg2, gg3)[, max_idx int32 (N,C,H,W)]"""
     N, C, D, H, W = x.shape
     L = _lib.lib()
+    for t in (x, g0, g1, g2, g3, grad_out):
+        ptr(t)
     with torch.cuda.device_of(x):
         gi = torch.empty_like(x)
         gg = [torch.empty_like(g0) for _ in range(4)]
