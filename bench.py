@@ -55,6 +55,39 @@ def lga2_bytes_per_voxel(D):
     return 20.0 + 900.0 / D
 
 
+def dist_setup(backend, device=None):
+    """One process per GPU (torchrun env); returns (world, rank, local_rank)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return world, rank, local_rank
+
+
+def max_over_ranks(value, world, device="cpu"):
+    """Job time = the slowest rank's device time (never a wall clock)."""
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, world, device="cpu"):
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -276,15 +309,12 @@ def run_ours(a):
     import torch.distributed as dist
     from ganet_b200 import ops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local_rank = dist_setup("nccl", dev)
     B, C, D, H, W = a.batch, a.channels, a.depth, a.height, a.width
     mine = shard_samples(B, world, rank)
     v_sga, v_lga = B * C * D * H * W, B * D * H * W
@@ -337,10 +367,9 @@ def run_ours(a):
     sync_all()
     ms = t0.elapsed_time(t1)
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = max_over_ranks(ms, world, dev)
+    done = sum_over_ranks(len(mine), world, dev)       # every sample processed exactly once
+    assert int(done) == B, (done, B)
     value = (v_sga + v_lga) * a.steps / (ms * 1e-3)
 
     # per-phase device time on this rank (events sit on the launch stream)
@@ -468,10 +497,7 @@ def run_e2e(torch, dist, world, dev, a, mine, v_sga, v_lga):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     wall = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = max_over_ranks(ms, world, dev)
     return {"value": (v_sga + v_lga) * steps / (ms * 1e-3), "unit": "voxels/s",
             "h2d_bytes_per_step": h2d * len(mine) * world, "d2h_bytes_per_step": d2h * len(mine) * world,
             "steps": steps, "ms_per_step": ms / steps, "wall_s": wall,

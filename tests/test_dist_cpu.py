@@ -1,0 +1,60 @@
+"""World-size-2 gloo test (CPU) of the multi-rank plumbing bench.py uses: the batch
+shard plan (rank r owns [r*B/G, (r+1)*B/G), no data-path collective),
+the max-over-ranks job time and the all-samples-processed-once check."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import bench
+    w, r, _ = bench.dist_setup("gloo")
+    assert (w, r) == (world, rank)
+    mine = bench.shard_samples(batch, w, r)
+    # each rank "processes" its shard: a per-sample checksum stands in for the kernels
+    local = sum(float(s + 1) for s in mine)
+    total = bench.sum_over_ranks(local, w)
+    count = bench.sum_over_ranks(len(mine), w)
+    slowest = bench.max_over_ranks(10.0 + rank, w)          # rank 1 is the slow one
+    gathered = [None] * w
+    dist.all_gather_object(gathered, mine)
+    if r == 0:
+        out.put((total, count, slowest, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_plan_and_timing_reduction():
+    world, batch = 2, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, q)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    total, count, slowest, gathered = q.get()
+    assert count == batch
+    assert total == sum(range(1, batch + 1))                # every sample exactly once
+    assert slowest == 11.0                                  # max over ranks, not rank 0's clock
+    assert gathered == [[0, 1, 2, 3], [4, 5, 6, 7]]
+
+
+def test_shard_plan_uneven():
+    import bench
+    for world in (1, 2, 3, 4, 8):
+        seen = sorted(s for r in range(world) for s in bench.shard_samples(8, world, r))
+        assert seen == list(range(8))
+        sizes = [len(bench.shard_samples(8, world, r)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
