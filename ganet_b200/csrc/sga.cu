@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "sga_step.cuh"
 #include "sga_vert.cuh"
+#include "sga_tma.cuh"
 #include "transpose.cuh"
 
 namespace ganet {
@@ -480,6 +481,119 @@ static int launch_vert_bwd(VCfg c, const float *x, const float *g, const float *
     return GANET_OK;
 }
 
+// ---- TMA-staged variants of the vertical kernels -----------------------------------------
+constexpr int kNotApplicable = -100;          // internal: fall back to the LDG kernels
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
+static bool tma_enabled()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("GANET_NO_TMA") ? 0 : 1;
+    return v != 0;
+}
+
+template <int MODE>
+static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, uint8_t *mask, int dir,
+                          MaskIds ids, int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    constexpr bool kCombine = (MODE == VMODE_SECOND || MODE == VMODE_COMBINE);
+    if (!tma_enabled() || D > 256 || (W % 4) != 0 || (kCombine && (W % 16) != 0)) return kNotApplicable;
+    const FwdPlan pl = fwd_plan(D, kCombine);
+    const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
+    int S = (kSmemBudget - ex_bytes - 128) / pl.stage_bytes;
+    if (S > 6) S = 6;
+    if (S > H) S = H;
+    if (S < 2 && H >= 2) return kNotApplicable;
+    const size_t smem = (size_t)S * pl.stage_bytes + ex_bytes + 2 * S * sizeof(uint64_t);
+    TmaFwdMaps maps;
+    if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, 32, 5)) return kNotApplicable;
+    if (!make_plane_map(&maps.out, out, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (kCombine) {
+        if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    } else {
+        maps.mask = maps.out;
+    }
+    const int strips = (W + 31) / 32;
+    const long long blocks = n_slices * strips;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const bool full = c.K * c.NW == D;
+#define X(K_, W_)                                                                              \
+    if (c.K == K_ && c.NW <= W_) {                                                             \
+        auto kf = sga_tma_fwd_kernel<K_, W_, MODE, true>;                                      \
+        auto kp = sga_tma_fwd_kernel<K_, W_, MODE, false>;                                     \
+        auto k = full ? kf : kp;                                                               \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+            cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
+        k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, dir, ids, D, H, strips, S);   \
+    } else
+    GANET_VERT_CFGS(X) { return kNotApplicable; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int launch_tma_bwd(VCfg c, const float *x, const float *g, const float *a, const uint8_t *mask,
+                          const float *go, float *gi, float *gg, int dir, int mask_id, int accumulate,
+                          int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    if (!tma_enabled() || D > 256 || (W % 16) != 0) return kNotApplicable;
+    const BwdPlan pl = bwd_plan(D);
+    const int ex_bytes = 2 * NBW * c.NW * 32 * 4;
+    int S = (kSmemBudget - ex_bytes - 128) / pl.stage_bytes;
+    if (S > 4) S = 4;
+    if (S > H) S = H;
+    if (S < 2 && H >= 2) return kNotApplicable;
+    const size_t smem = (size_t)S * pl.stage_bytes + ex_bytes + 2 * S * sizeof(uint64_t);
+    TmaBwdMaps maps;
+    if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, 32, 5)) return kNotApplicable;
+    if (!make_plane_map(&maps.a, a, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (!make_plane_map(&maps.go, go, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (!make_plane_map(&maps.gi, gi, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, 32, D)) return kNotApplicable;
+    const int strips = (W + 31) / 32;
+    const long long blocks = n_slices * strips;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const bool full = c.K * c.NW == D;
+#define X(K_, W_)                                                                              \
+    if (c.K == K_ && c.NW <= W_) {                                                             \
+        auto kf = sga_tma_bwd_kernel<K_, W_, true>;                                            \
+        auto kp = sga_tma_bwd_kernel<K_, W_, false>;                                           \
+        auto k = full ? kf : kp;                                                               \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+            cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
+        k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, gi, gg, dir, mask_id,         \
+                                                           accumulate, D, H, W, strips, S);    \
+    } else
+    GANET_VERT_CFGS(X) { return kNotApplicable; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+// front doors: TMA when the shape allows it, else the LDG kernels
+template <int MODE>
+static int run_vert_fwd(VCfg c, const float *x, const float *g, float *out, uint8_t *mask, int dir,
+                        MaskIds ids, int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    const int rc = launch_tma_fwd<MODE>(c, x, g, out, mask, dir, ids, D, H, W, n_slices, st);
+    if (rc != kNotApplicable) return rc;
+    return launch_vert_fwd<MODE>(c, x, g, out, mask, dir, ids, D, H, W, n_slices, st);
+}
+
+static int run_vert_bwd(VCfg c, const float *x, const float *g, const float *a, const uint8_t *mask,
+                        const float *go, float *gi, float *gg, int dir, int mask_id, int accumulate,
+                        int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    const int rc = launch_tma_bwd(c, x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W,
+                                  n_slices, st);
+    if (rc != kNotApplicable) return rc;
+    return launch_vert_bwd(c, x, g, a, mask, go, gi, gg, dir, mask_id, accumulate, D, H, W, n_slices, st);
+}
+
 static int check_dims(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
     if (N <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return GANET_EINVAL;
@@ -602,13 +716,13 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
         if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(g_right + s0 * 5 * HW, gT2, n * 5, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(g_left + s0 * 5 * HW, gT3, n * 5, iH, iW, st))) return rc;
-        if ((rc = launch_vert_fwd<VMODE_FIRST>(vc, xT, gT2, outT, maskT, 0, MaskIds{2, 2}, iD, iW, iH, n, st))) return rc;
-        if ((rc = launch_vert_fwd<VMODE_SECOND>(vc, xT, gT3, outT, maskT, 1, MaskIds{2, 3}, iD, iW, iH, n, st))) return rc;
+        if ((rc = run_vert_fwd<VMODE_FIRST>(vc, xT, gT2, outT, maskT, 0, MaskIds{2, 2}, iD, iW, iH, n, st))) return rc;
+        if ((rc = run_vert_fwd<VMODE_SECOND>(vc, xT, gT3, outT, maskT, 1, MaskIds{2, 3}, iD, iW, iH, n, st))) return rc;
         if ((rc = launch_transpose<float, false>(outT, os, n * D, iW, iH, st))) return rc;
         if ((rc = launch_transpose<uint8_t, false>(maskT, ms, n * D, iW, iH, st))) return rc;
         // vertical scans merge on top; the tie rule keeps the lower direction id
-        if ((rc = launch_vert_fwd<VMODE_COMBINE>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
-        if ((rc = launch_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st))) return rc;
+        if ((rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+        if ((rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st))) return rc;
     }
     return GANET_OK;
 }
@@ -623,7 +737,7 @@ GANET_API int ganet_sga_direction(const float *x, const float *g, float *a, int 
     Cfg c;
     VCfg vc;
     if (dir < 2 && pick_vert_cfg((int)D, &vc))
-        return launch_vert_fwd<VMODE_RAW>(vc, x, g, a, nullptr, dir, MaskIds{0, 0}, (int)D, (int)H,
+        return run_vert_fwd<VMODE_RAW>(vc, x, g, a, nullptr, dir, MaskIds{0, 0}, (int)D, (int)H,
                                           (int)W, N * C, (cudaStream_t)stream);
     if (!pick_cfg((int)D, dir < 2, &c)) return GANET_EUNSUPPORTED;
     return launch_fwd<MODE_RAW>(c, x, g, a, nullptr, dir, (int)D, (int)H, (int)W, N * C,
@@ -695,8 +809,8 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
         float *gis = grad_in + s0 * S;
         // vertical directions in place
         for (int dir = 0; dir < 2; dir++) {
-            if ((rc = launch_vert_fwd<VMODE_RAW>(vc, xs, g[dir] + s0 * 5 * HW, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
-            if ((rc = launch_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, a, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g[dir] + s0 * 5 * HW, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+            if ((rc = run_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, a, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
         }
         // horizontal directions on the transposed slices
         if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
@@ -704,13 +818,13 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
         if ((rc = launch_transpose<uint8_t, false>(ms, maskT, n * D, iH, iW, st))) return rc;
         for (int dir = 2; dir < 4; dir++) {
             if ((rc = launch_transpose<float, false>(g[dir] + s0 * 5 * HW, gT, n * 5, iH, iW, st))) return rc;
-            if ((rc = launch_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
             if (max_idx && dir == 2) {
                 dim3 grid((unsigned)((HW + 255) / 256), (unsigned)n);
                 max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(a, max_idx + s0 * HW, iD, iH, iW);
                 GANET_RETURN_IF_LAUNCH_FAILED();
             }
-            if ((rc = launch_vert_bwd(vc, xT, gT, a, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
+            if ((rc = run_vert_bwd(vc, xT, gT, a, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
             if ((rc = launch_transpose<float, false>(ggT, gg[dir] + s0 * 5 * HW, n * 5, iW, iH, st))) return rc;
         }
         if ((rc = launch_transpose<float, true>(giT, gis, n * D, iW, iH, st))) return rc;   // gi += giT^T

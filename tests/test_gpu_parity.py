@@ -43,7 +43,11 @@ def ops():
 # chunking), config 1 of BASELINE.json, and the model's 1/6-resolution D=33
 SGA_SHAPES = [(2, 3, 7, 5, 6), (1, 2, 1, 4, 3), (1, 1, 2, 1, 5), (1, 2, 3, 6, 1), (1, 1, 1, 1, 1),
               (1, 2, 9, 8, 10), (1, 1, 33, 9, 13), (1, 2, 65, 6, 11), (1, 1, 192, 5, 9),
-              (1, 1, 288, 3, 5), (1, 1, 100, 4, 35), (1, 8, 48, 48, 96)]
+              (1, 1, 288, 3, 5), (1, 1, 100, 4, 35), (1, 8, 48, 48, 96),
+              # H and W multiples of 16: the TMA-staged kernels run in both layouts; partial
+              # 32-column strips (48, 80), depth not filling the last warp (65, 33), one stage
+              (1, 2, 24, 16, 48), (2, 2, 65, 32, 80), (1, 1, 192, 16, 32), (1, 2, 33, 16, 16),
+              (1, 1, 256, 16, 16)]
 
 
 @needs_ref
@@ -105,7 +109,7 @@ def test_sga_backward_vs_reference_cuda(ops, shape):
         assert_close(npy(gg[d]), npy(rgg[d]), RTOL, "guidance grad %d" % d)
 
 
-@pytest.mark.parametrize("shape", SGA_SHAPES[:8])
+@pytest.mark.parametrize("shape", SGA_SHAPES[:8] + SGA_SHAPES[12:15])
 def test_sga_backward_vs_oracle(ops, shape):
     x, g, go = sga_inputs(shape, seed=4 + sum(shape))
     xt, gt = cu(x), [cu(a) for a in g]
@@ -148,6 +152,35 @@ def test_sga_against_golden_vectors(ops):
         assert_close(npy(gi), z[f"gi{k}"], RTOL, "gradInput")
         for d in range(4):
             assert_close(npy(gg[d]), z[f"gg{k}_{d}"], RTOL, "guidance grad")
+
+
+def test_tma_and_ldg_kernels_agree_bitwise(ops):
+    """GANET_NO_TMA is read once per process, so compare through a subprocess: the plain
+    load/store kernels and the TMA-staged ones must give identical bits."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+        "from ganet_b200 import ops; from util import sga_inputs;"
+        "x, g, go = sga_inputs((1, 2, 24, 32, 48), seed=77);"
+        "cu = lambda a: torch.from_numpy(a).cuda();"
+        "xt, gt = cu(x), [cu(a) for a in g];"
+        "out, mask = ops.sga_forward(xt, *gt);"
+        "gi, gg = ops.sga_backward(xt, *gt, mask, cu(go));"
+        "h = hashlib.sha256();"
+        "[h.update(t.cpu().numpy().tobytes()) for t in (out, mask, gi) + tuple(gg)];"
+        "print(h.hexdigest())"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for no_tma in ("", "1"):
+        env = dict(os.environ)
+        env.pop("GANET_NO_TMA", None)
+        if no_tma:
+            env["GANET_NO_TMA"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
 
 
 def test_sga_ties_and_constant_input(ops):
