@@ -21,65 +21,106 @@ namespace ganet {
 
 constexpr int kLgaThreads = 128;
 
+// All three kernels iterate over INPUT depth planes: the (2R+1)^2 neighbourhood of plane dp
+// is loaded once (25 loads for R=2) and used for the three depth taps it feeds, so a voxel
+// costs 25 loads + 75 FMAs instead of 75 + 75.  Taps whose (r,c) leaves the image are given
+// weight 0 (their load is redirected to the pixel itself) and their true contribution --
+// always "centre voxel times tap weight" (:1162-1165) -- is added as one term per output.
+
+template <int R>
+struct LgaGeom {
+    static constexpr int WS = 2 * R + 1, P2 = WS * WS, F = 3 * P2;
+};
+
+// in-plane validity + clamped neighbour offsets of this pixel
+template <int R>
+__device__ __forceinline__ void lga_taps(int h, int w, int H, int W, bool (&ok)[LgaGeom<R>::P2],
+                                         int (&noff)[LgaGeom<R>::P2])
+{
+    constexpr int WS = LgaGeom<R>::WS;
+#pragma unroll
+    for (int r = -R; r <= R; r++)
+#pragma unroll
+        for (int c = -R; c <= R; c++) {
+            const int t = (r + R) * WS + (c + R);
+            ok[t] = (h + r >= 0) && (h + r < H) && (w + c >= 0) && (w + c < W);
+            noff[t] = ok[t] ? r * W + c : 0;
+        }
+}
+
 // ---- forward ---------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kLgaThreads)
 lga_fwd_kernel(const float *__restrict__ x, const float *__restrict__ f, float *__restrict__ y,
                int D, int H, int W, int d_chunk)
 {
-    constexpr int WS = 2 * R + 1, P2 = WS * WS, F = 3 * P2;
+    constexpr int P2 = LgaGeom<R>::P2, F = LgaGeom<R>::F;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
-    const long long b = blockIdx.z / ((D + d_chunk - 1) / d_chunk);
-    const int dc = blockIdx.z % ((D + d_chunk - 1) / d_chunk);
+    const int nchunk = (D + d_chunk - 1) / d_chunk;
+    const long long b = blockIdx.z / nchunk;
+    const int dc = blockIdx.z % nchunk;
     if (w >= W) return;
     const int HW = H * W;
-    const float *xb = x + b * (long long)D * HW;
-    float *yb = y + b * (long long)D * HW;
+    const float *xb = x + b * (long long)D * HW + h * W + w;
+    float *yb = y + b * (long long)D * HW + h * W + w;
     const float *fb = f + b * (long long)F * HW + h * W + w;
 
-    float wt[F];
-#pragma unroll
-    for (int l = 0; l < F; l++) wt[l] = ld_nc(fb + (long long)l * HW);
-
-    // in-plane validity of every (r, c) tap for this pixel
     bool ok[P2];
+    int noff[P2];
+    lga_taps<R>(h, w, H, W, ok, noff);
+    float wz[F];                 // tap weights, 0 where (r,c) leaves the image
+    float cval[3] = {0.f, 0.f, 0.f};   // per depth tap: sum of the in-image weights
+    float coob = 0.f;            // sum of all out-of-image weights (all three depth taps)
 #pragma unroll
-    for (int r = -R; r <= R; r++)
+    for (int dd = 0; dd < 3; dd++)
 #pragma unroll
-        for (int c = -R; c <= R; c++)
-            ok[(r + R) * WS + (c + R)] = (h + r >= 0) && (h + r < H) && (w + c >= 0) && (w + c < W);
+        for (int t = 0; t < P2; t++) {
+            const float v = ld_nc(fb + (long long)(dd * P2 + t) * HW);
+            wz[dd * P2 + t] = ok[t] ? v : 0.f;
+            if (ok[t]) cval[dd] += v; else coob += v;
+        }
 
     const int dbeg = dc * d_chunk, dend = min(D, dbeg + d_chunk);
-    for (int d = dbeg; d < dend; d++) {
-        const float *xc = xb + (long long)d * HW + h * W + w;
-        const float ctr = ld_nc(xc);
-        float acc = 0.f;
+    // rolling outputs: a0 = y[dp-1] (complete after plane dp), a1 = y[dp], a2 = y[dp+1]
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float cprev = 0.f;           // centre value of plane dp-1
+    for (int dp = max(dbeg - 1, 0); dp < min(dend + 1, D); dp++) {
+        const float *xp = xb + (long long)dp * HW;
+        const float ctr = ld_nc(xp);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f;      // contributions of this plane to y[dp+1], y[dp], y[dp-1]
 #pragma unroll
-        for (int dd = -1; dd <= 1; dd++) {
-            const bool dok = (d + dd >= 0) && (d + dd < D);
-#pragma unroll
-            for (int r = -R; r <= R; r++)
-#pragma unroll
-                for (int c = -R; c <= R; c++) {
-                    const int t = (r + R) * WS + (c + R);
-                    const float v = (dok && ok[t]) ? ld_nc(xc + dd * HW + r * W + c) : ctr;
-                    acc = fmaf(v, wt[(dd + 1) * P2 + t], acc);
-                }
+        for (int t = 0; t < P2; t++) {
+            const float v = ld_nc(xp + noff[t]);
+            n0 = fmaf(v, wz[0 * P2 + t], n0);    // depth tap -1 of output dp+1
+            n1 = fmaf(v, wz[1 * P2 + t], n1);    // depth tap  0 of output dp
+            n2 = fmaf(v, wz[2 * P2 + t], n2);    // depth tap +1 of output dp-1
         }
-        yb[(long long)d * HW + h * W + w] = acc;
+        a0 += n2; a1 += n1; a2 += n0;
+        // centre-fallback terms of output dp (its own centre): out-of-image taps always,
+        // plus the whole -1 / +1 depth tap at the volume faces
+        float fb_w = coob;
+        if (dp == 0) fb_w += cval[0];
+        if (dp == D - 1) fb_w += cval[2];
+        a1 = fmaf(ctr, fb_w, a1);
+        if (dp - 1 >= dbeg && dp - 1 < dend) yb[(long long)(dp - 1) * HW] = a0;
+        a0 = a1; a1 = a2; a2 = 0.f;
+        cprev = ctr;
     }
+    (void)cprev;
+    const int last = min(dend + 1, D) - 1;       // plane index processed last
+    if (last >= dbeg && last < dend) yb[(long long)last * HW] = a0;   // only when dend == D
 }
 
 // ---- backward: filter gradient (:1177-1216) ---------------------------------
-// one thread per pixel accumulates all F taps over a depth chunk; chunks are
-// combined with atomics only when D is split (d_chunk < D).
+// gf[dd][t] = sum_d go[d] * (x[d+dd] at neighbour t, or the centre x[d] when that voxel is
+// outside).  One thread per pixel, all depths; 75 accumulators in registers.
 template <int R>
 __global__ void __launch_bounds__(kLgaThreads)
 lga_bwd_filter_kernel(const float *__restrict__ x, const float *__restrict__ go,
                       float *__restrict__ gf, int accumulate, int D, int H, int W)
 {
-    constexpr int WS = 2 * R + 1, P2 = WS * WS, F = 3 * P2;
+    constexpr int P2 = LgaGeom<R>::P2, F = LgaGeom<R>::F;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
     const long long b = blockIdx.z;
@@ -90,108 +131,108 @@ lga_bwd_filter_kernel(const float *__restrict__ x, const float *__restrict__ go,
     float *gfb = gf + b * (long long)F * HW + h * W + w;
 
     bool ok[P2];
-#pragma unroll
-    for (int r = -R; r <= R; r++)
-#pragma unroll
-        for (int c = -R; c <= R; c++)
-            ok[(r + R) * WS + (c + R)] = (h + r >= 0) && (h + r < H) && (w + c >= 0) && (w + c < W);
-
+    int noff[P2];
+    lga_taps<R>(h, w, H, W, ok, noff);
     float acc[F];
 #pragma unroll
     for (int l = 0; l < F; l++) acc[l] = 0.f;
 
-    for (int d = 0; d < D; d++) {
-        const float g0 = ld_nc(gb + (long long)d * HW);
-        const float *xc = xb + (long long)d * HW;
-        const float ctr = ld_nc(xc);
+    // plane dp of x meets go[dp+1] (depth tap -1), go[dp] (tap 0), go[dp-1] (tap +1)
+    float gm = 0.f;                               // go[dp-1]
+    float gc = ld_nc(gb);                         // go[dp]
+    float sgc = 0.f, e_first = 0.f, e_last = 0.f; // sum go*x centre; face terms
+    for (int dp = 0; dp < D; dp++) {
+        const float gp = (dp + 1 < D) ? ld_nc(gb + (long long)(dp + 1) * HW) : 0.f;   // go[dp+1]
+        const float *xp = xb + (long long)dp * HW;
+        const float ctr = ld_nc(xp);
+        sgc = fmaf(gc, ctr, sgc);
+        if (dp == 0) e_first = gc * ctr;
+        if (dp == D - 1) e_last = gc * ctr;
 #pragma unroll
-        for (int dd = -1; dd <= 1; dd++) {
-            const bool dok = (d + dd >= 0) && (d + dd < D);
-#pragma unroll
-            for (int r = -R; r <= R; r++)
-#pragma unroll
-                for (int c = -R; c <= R; c++) {
-                    const int t = (r + R) * WS + (c + R);
-                    const float v = (dok && ok[t]) ? ld_nc(xc + dd * HW + r * W + c) : ctr;
-                    acc[(dd + 1) * P2 + t] = fmaf(g0, v, acc[(dd + 1) * P2 + t]);
-                }
+        for (int t = 0; t < P2; t++) {
+            const float v = ld_nc(xp + noff[t]);
+            acc[0 * P2 + t] = fmaf(gp, v, acc[0 * P2 + t]);
+            acc[1 * P2 + t] = fmaf(gc, v, acc[1 * P2 + t]);
+            acc[2 * P2 + t] = fmaf(gm, v, acc[2 * P2 + t]);
         }
+        gm = gc; gc = gp;
     }
 #pragma unroll
-    for (int l = 0; l < F; l++) {
-        float *dst = gfb + (long long)l * HW;
-        *dst = accumulate ? *dst + acc[l] : acc[l];
-    }
+    for (int dd = 0; dd < 3; dd++)
+#pragma unroll
+        for (int t = 0; t < P2; t++) {
+            // out-of-image tap: every depth falls back to the centre; in-image tap: only the
+            // face depth whose d+dd leaves the volume does
+            float v = ok[t] ? acc[dd * P2 + t] + (dd == 0 ? e_first : dd == 2 ? e_last : 0.f) : sgc;
+            float *dst = gfb + (long long)(dd * P2 + t) * HW;
+            *dst = accumulate ? *dst + v : v;
+        }
 }
 
 // ---- backward: data gradient (:1218-1269) -----------------------------------
 // gx[v] = sum over taps: neighbour u = v + tap in range ? go[u] * f[loc(-tap) at u]
 //                                                        : go[v] * f[loc(tap) at v]
+// Same rolling structure as the forward with the mirrored weights of the neighbours.
 template <int R>
 __global__ void __launch_bounds__(kLgaThreads)
 lga_bwd_data_kernel(const float *__restrict__ f, const float *__restrict__ go,
                     float *__restrict__ gx, int D, int H, int W, int d_chunk)
 {
-    constexpr int WS = 2 * R + 1, P2 = WS * WS, F = 3 * P2;
+    constexpr int WS = LgaGeom<R>::WS, P2 = LgaGeom<R>::P2, F = LgaGeom<R>::F;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
-    const long long b = blockIdx.z / ((D + d_chunk - 1) / d_chunk);
-    const int dc = blockIdx.z % ((D + d_chunk - 1) / d_chunk);
+    const int nchunk = (D + d_chunk - 1) / d_chunk;
+    const long long b = blockIdx.z / nchunk;
+    const int dc = blockIdx.z % nchunk;
     if (w >= W) return;
     const int HW = H * W;
     const float *gb = go + b * (long long)D * HW + h * W + w;
     float *gxb = gx + b * (long long)D * HW + h * W + w;
     const float *fb = f + b * (long long)F * HW + h * W + w;
 
-    // Filters gathered from the neighbour pixels: for an in-plane-valid tap (r,c)
-    // the mirrored tap of pixel (h+r, w+c).  Every fallback term multiplies the
-    // same centre value go[d,h,w], so their weights are pre-summed per depth tap.
-    float wn[F];       // weight applied to go[d+dd, h+r, w+c]
-    float cplane[3];   // sum of this pixel's taps of plane dd      (used when d+dd is out of range)
-    float coob[3];     // sum of this pixel's taps with (r,c) outside the image (plane in range)
     bool ok[P2];
-#pragma unroll
-    for (int dd = 0; dd < 3; dd++) { cplane[dd] = 0.f; coob[dd] = 0.f; }
+    int noff[P2];
+    lga_taps<R>(h, w, H, W, ok, noff);
+    float wn[F];                 // mirrored weight of the neighbour pixel, 0 outside the image
+    float cval[3] = {0.f, 0.f, 0.f};   // this pixel's own in-image weights per depth tap
+    float coob = 0.f;                  // this pixel's own out-of-image weights
 #pragma unroll
     for (int r = -R; r <= R; r++)
 #pragma unroll
         for (int c = -R; c <= R; c++) {
             const int t = (r + R) * WS + (c + R);
-            ok[t] = (h + r >= 0) && (h + r < H) && (w + c >= 0) && (w + c < W);
 #pragma unroll
             for (int dd = -1; dd <= 1; dd++) {
                 const int loc_m = (-dd + 1) * P2 + (-r + R) * WS + (-c + R);
                 wn[(dd + 1) * P2 + t] = ok[t] ? ld_nc(fb + r * W + c + (long long)loc_m * HW) : 0.f;
                 const float own = ld_nc(fb + (long long)((dd + 1) * P2 + t) * HW);
-                cplane[dd + 1] += own;
-                if (!ok[t]) coob[dd + 1] += own;
+                if (ok[t]) cval[dd + 1] += own; else coob += own;
             }
         }
 
     const int dbeg = dc * d_chunk, dend = min(D, dbeg + d_chunk);
-    for (int d = dbeg; d < dend; d++) {
-        const float *gc = gb + (long long)d * HW;
-        const float ctr = ld_nc(gc);
-        float acc = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int dp = max(dbeg - 1, 0); dp < min(dend + 1, D); dp++) {
+        const float *gp = gb + (long long)dp * HW;
+        const float ctr = ld_nc(gp);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 #pragma unroll
-        for (int dd = -1; dd <= 1; dd++) {
-            const bool dok = (d + dd >= 0) && (d + dd < D);
-            if (dok) {
-#pragma unroll
-                for (int r = -R; r <= R; r++)
-#pragma unroll
-                    for (int c = -R; c <= R; c++) {
-                        const int t = (r + R) * WS + (c + R);
-                        const float v = ok[t] ? ld_nc(gc + dd * HW + r * W + c) : 0.f;
-                        acc = fmaf(v, wn[(dd + 1) * P2 + t], acc);
-                    }
-                acc = fmaf(ctr, coob[dd + 1], acc);
-            } else {
-                acc = fmaf(ctr, cplane[dd + 1], acc);
-            }
+        for (int t = 0; t < P2; t++) {
+            const float v = ld_nc(gp + noff[t]);
+            n0 = fmaf(v, wn[0 * P2 + t], n0);    // go plane dp is the dd=-1 neighbour of output dp+1
+            n1 = fmaf(v, wn[1 * P2 + t], n1);
+            n2 = fmaf(v, wn[2 * P2 + t], n2);    // ... and the dd=+1 neighbour of output dp-1
         }
-        gxb[(long long)d * HW] = acc;
+        a0 += n2; a1 += n1; a2 += n0;
+        float fb_w = coob;
+        if (dp == 0) fb_w += cval[0];
+        if (dp == D - 1) fb_w += cval[2];
+        a1 = fmaf(ctr, fb_w, a1);
+        if (dp - 1 >= dbeg && dp - 1 < dend) gxb[(long long)(dp - 1) * HW] = a0;
+        a0 = a1; a1 = a2; a2 = 0.f;
     }
+    const int last = min(dend + 1, D) - 1;
+    if (last >= dbeg && last < dend) gxb[(long long)last * HW] = a0;
 }
 
 static int pick_d_chunk(int64_t B, int64_t D, int64_t H, int64_t W)
