@@ -719,7 +719,7 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
         if ((rc = run_vert_fwd<VMODE_FIRST>(vc, xT, gT2, outT, maskT, 0, MaskIds{2, 2}, iD, iW, iH, n, st))) return rc;
         if ((rc = run_vert_fwd<VMODE_SECOND>(vc, xT, gT3, outT, maskT, 1, MaskIds{2, 3}, iD, iW, iH, n, st))) return rc;
         if ((rc = launch_transpose<float, false>(outT, os, n * D, iW, iH, st))) return rc;
-        if ((rc = launch_transpose<uint8_t, false>(maskT, ms, n * D, iW, iH, st))) return rc;
+        if ((rc = launch_transpose_u8(maskT, ms, n * D, iW, iH, st))) return rc;
         // vertical scans merge on top; the tie rule keeps the lower direction id
         if ((rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
         if ((rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st))) return rc;
@@ -815,7 +815,7 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
         // horizontal directions on the transposed slices
         if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(gos, goT, n * D, iH, iW, st))) return rc;
-        if ((rc = launch_transpose<uint8_t, false>(ms, maskT, n * D, iH, iW, st))) return rc;
+        if ((rc = launch_transpose_u8(ms, maskT, n * D, iH, iW, st))) return rc;
         for (int dir = 2; dir < 4; dir++) {
             if ((rc = launch_transpose<float, false>(g[dir] + s0 * 5 * HW, gT, n * 5, iH, iW, st))) return rc;
             if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
