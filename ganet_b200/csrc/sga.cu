@@ -494,11 +494,13 @@ static bool tma_enabled()
 
 template <int MODE>
 static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, uint8_t *mask, int dir,
-                          MaskIds ids, int D, int H, int W, long long n_slices, cudaStream_t st)
+                          MaskIds ids, int D, int H, int W, long long n_slices, cudaStream_t st,
+                          const float *a2 = nullptr, const float *a3 = nullptr)
 {
-    constexpr bool kCombine = (MODE == VMODE_SECOND || MODE == VMODE_COMBINE);
+    constexpr bool kThree = (MODE == VMODE_FIRST3);
+    constexpr bool kCombine = (MODE == VMODE_SECOND || MODE == VMODE_COMBINE || kThree);
     if (!tma_enabled() || D > 256 || (W % 4) != 0 || (kCombine && (W % 16) != 0)) return kNotApplicable;
-    const FwdPlan pl = fwd_plan(D, kCombine);
+    const FwdPlan pl = fwd_plan(D, kCombine, kThree);
     const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
     int S = (kSmemBudget - ex_bytes - 128) / pl.stage_bytes;
     if (S > 6) S = 6;
@@ -513,6 +515,13 @@ static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, ui
         if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, 32, D)) return kNotApplicable;
     } else {
         maps.mask = maps.out;
+    }
+    maps.a2 = maps.out;
+    maps.a3 = maps.out;
+    if (kThree) {
+        if (!a2 || !a3) return GANET_EINVAL;
+        if (!make_plane_map(&maps.a2, a2, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
+        if (!make_plane_map(&maps.a3, a3, 4, n_slices * D, H, W, 32, D)) return kNotApplicable;
     }
     const int strips = (W + 31) / 32;
     const long long blocks = n_slices * strips;
@@ -572,6 +581,58 @@ static int launch_tma_bwd(VCfg c, const float *x, const float *g, const float *a
 #undef X
     GANET_RETURN_IF_LAUNCH_FAILED();
     return GANET_OK;
+}
+
+// horizontal aggregate in the standard layout (no transposes), DIR 0 = right, 1 = left
+template <int DIR>
+static int launch_tma_hraw(VCfg c, const float *x, const float *g, float *out, int D, int H, int W,
+                           long long n_slices, cudaStream_t st)
+{
+    if (!tma_enabled() || D > 256 || (W % 4) != 0 || H < 32) return kNotApplicable;
+    const int stage_bytes = D * 512 + 2560;
+    const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
+    int S = (kSmemBudget - ex_bytes - 128) / stage_bytes;
+    if (S > 4) S = 4;
+    if (S > W / 4) S = W / 4;
+    if (S < 2) return kNotApplicable;
+    const size_t smem = (size_t)S * stage_bytes + ex_bytes + 2 * S * sizeof(uint64_t);
+    TmaHrawMaps maps;
+    if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, 4, D, 32)) return kNotApplicable;
+    if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, 4, 5, 32)) return kNotApplicable;
+    if (!make_plane_map(&maps.out, out, 4, n_slices * D, H, W, 4, D, 32)) return kNotApplicable;
+    const int strips = (H + 31) / 32;
+    const long long blocks = n_slices * strips;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const bool full = c.K * c.NW == D;
+#define X(K_, W_)                                                                              \
+    if (c.K == K_ && c.NW <= W_) {                                                             \
+        auto kf = sga_tma_hraw_kernel<K_, W_, DIR, true>;                                      \
+        auto kp = sga_tma_hraw_kernel<K_, W_, DIR, false>;                                     \
+        auto k = full ? kf : kp;                                                               \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+            cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
+        k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, D, W, strips, S);             \
+    } else
+    GANET_VERT_CFGS(X) { return kNotApplicable; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+// Should the transpose-free forward (hraw x2 + FIRST3 + COMBINE, 4 launches instead of 9) run?
+// Its boxes have a 16-byte inner extent: 6144 tiny TMA requests per box, which is request-rate
+// bound once the volume no longer sits in L2.  Measured on B200 (profiles/): faster up to
+// ~35M voxels per call (1x32x65x80x208: 0.72 vs 0.85 ms; 1x48x33x64x208: 0.38 vs 0.52 ms),
+// slower beyond (1x32x192x240x624: 33.8 vs 12.8 ms) -- so it is used for small calls only.
+static bool fwd_direct_ok(VCfg c, int D, int H, int W, long long voxels)
+{
+    if (!tma_enabled() || getenv("GANET_NO_DIRECT") || D > 256 || (W % 16) != 0 || H < 32) return false;
+    if (voxels > 48ll * 1000 * 1000 && !getenv("GANET_FORCE_DIRECT")) return false;
+    const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
+    if ((kSmemBudget - ex_bytes - 128) / (D * 512 + 2560) < 2) return false;
+    if ((kSmemBudget - ex_bytes - 128) / fwd_plan(D, true, true).stage_bytes < 2) return false;
+    return get_encode_tiled() != nullptr;
 }
 
 // front doors: TMA when the shape allows it, else the LDG kernels
@@ -712,6 +773,22 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
         const float *xs = x + s0 * S;
         float *os = out + s0 * S;
         uint8_t *ms = mask + s0 * S;
+        if (fwd_direct_ok(vc, iD, iH, iW, n * S)) {
+            // transpose-free: right and left aggregates straight from the standard layout into
+            // scratch, then `down` merges all three, then `up` merges on top
+            float *a2 = xT, *a3 = outT;
+            rc = launch_tma_hraw<0>(vc, xs, g_right + s0 * 5 * HW, a2, iD, iH, iW, n, st);
+            if (rc == GANET_OK) rc = launch_tma_hraw<1>(vc, xs, g_left + s0 * 5 * HW, a3, iD, iH, iW, n, st);
+            if (rc == GANET_OK)
+                rc = launch_tma_fwd<VMODE_FIRST3>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH,
+                                                  iW, n, st, a2, a3);
+            if (rc == GANET_OK)
+                rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st);
+            if (rc != kNotApplicable) {
+                if (rc) return rc;
+                continue;
+            }
+        }
         // horizontal scans = vertical scans of the H<->W transposed slices
         if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(g_right + s0 * 5 * HW, gT2, n * 5, iH, iW, st))) return rc;

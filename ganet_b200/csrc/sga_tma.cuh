@@ -29,21 +29,23 @@
 
 namespace ganet {
 
-struct TmaFwdMaps { CUtensorMap x, g, out, mask; };
+struct TmaFwdMaps { CUtensorMap x, g, out, mask, a2, a3; };   // a2/a3: FIRST3 inputs
+struct TmaHrawMaps { CUtensorMap x, g, out; };
 struct TmaBwdMaps { CUtensorMap x, g, a, mask, go, gi; };
 
 __host__ __device__ inline int align128(int v) { return (v + 127) & ~127; }
 
 // ---- shared-memory plan (host and device agree through these helpers) ------------------
-struct FwdPlan { int off_x, off_o, off_m, off_g, stage_bytes; };
-__host__ __device__ inline FwdPlan fwd_plan(int D, bool combine)
+struct FwdPlan { int off_x, off_o, off_m, off_a3, off_g, stage_bytes; };
+__host__ __device__ inline FwdPlan fwd_plan(int D, bool combine, bool three = false)
 {
     FwdPlan p;
     const int xb = D * 128;
     p.off_x = 0;
     p.off_o = xb;
     p.off_m = 2 * xb;
-    p.off_g = combine ? 2 * xb + align128(D * 32) : xb;
+    p.off_a3 = 2 * xb + align128(D * 32);
+    p.off_g = three ? p.off_a3 + xb : (combine ? p.off_a3 : xb);
     p.stage_bytes = p.off_g + 640;            // 5 guidance rows of 32 floats
     return p;
 }
@@ -70,14 +72,15 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
                    int strips, int S)
 {
     static_assert(K % 2 == 0, "depth parity must be a compile-time property");
-    constexpr bool kCombine = (MODE == VMODE_SECOND || MODE == VMODE_COMBINE);
+    constexpr bool kThree = (MODE == VMODE_FIRST3);       // merge down with the two horizontal aggregates
+    constexpr bool kCombine = (MODE == VMODE_SECOND || MODE == VMODE_COMBINE || kThree);
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
     const int NW = (blockDim.x >> 5) - 1;                 // consumer warps; warp NW is the producer
     const long long s = blockIdx.x / strips;
     const int strip = blockIdx.x - (int)(s * strips);
     const int w0 = strip * 32;
-    const FwdPlan pl = fwd_plan(D, kCombine);
+    const FwdPlan pl = fwd_plan(D, kCombine, kThree);
     const int plane = NW * 32;
     float *ex = reinterpret_cast<float *>(smem + (size_t)S * pl.stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * pl.stage_bytes + 2 * 3 * plane * 4);
@@ -93,7 +96,8 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
 
     if (j == NW) {                                        // ---------------- producer
         if (lane == 0) {
-            const unsigned tx = D * 128 + 640 + (kCombine ? D * 128 : 0) + (MODE == VMODE_COMBINE ? D * 32 : 0);
+            const unsigned tx = D * 128 + 640 + (kCombine ? D * 128 : 0) + (MODE == VMODE_COMBINE ? D * 32 : 0) +
+                                (kThree ? D * 128 : 0);
             auto issue = [&](int t) {
                 const int st = t % S;
                 const int h = (dir == 0) ? t : H - 1 - t;
@@ -101,7 +105,12 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
                 mbar_arrive_expect_tx(&full[st], tx);
                 tma_load_3d(b + pl.off_x, &maps.x, &full[st], w0, h, c2x);
                 tma_load_3d(b + pl.off_g, &maps.g, &full[st], w0, h, c2g);
-                if (kCombine) tma_load_3d(b + pl.off_o, &maps.out, &full[st], w0, h, c2x);
+                if (kThree) {
+                    tma_load_3d(b + pl.off_o, &maps.a2, &full[st], w0, h, c2x);
+                    tma_load_3d(b + pl.off_a3, &maps.a3, &full[st], w0, h, c2x);
+                } else if (kCombine) {
+                    tma_load_3d(b + pl.off_o, &maps.out, &full[st], w0, h, c2x);
+                }
                 if (MODE == VMODE_COMBINE) tma_load_3d(b + pl.off_m, &maps.mask, &full[st], w0, h, c2x);
             };
             for (int t = 0; t < S && t < H; t++) issue(t);
@@ -143,7 +152,7 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
         float *ot = reinterpret_cast<float *>(b + pl.off_o + toff);
         uint8_t *mt = b + pl.off_m + moff;
         const float *gt = reinterpret_cast<const float *>(b + pl.off_g) + lane;
-        float xc[K], w[5], oc[K];
+        float xc[K], w[5], oc[K], o3[K];
         uint8_t mc[K];
 #pragma unroll
         for (int i = 0; i < K; i++) xc[i] = (FULL || d0 + i < D) ? xt[i * 32] : 0.f;
@@ -152,6 +161,11 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
         if (kCombine) {
 #pragma unroll
             for (int i = 0; i < K; i++) oc[i] = (FULL || d0 + i < D) ? ot[i * 32] : 0.f;
+        }
+        if (kThree) {
+            const float *a3t = reinterpret_cast<const float *>(b + pl.off_a3 + toff);
+#pragma unroll
+            for (int i = 0; i < K; i++) o3[i] = (FULL || d0 + i < D) ? a3t[i * 32] : 0.f;
         }
         if (MODE == VMODE_COMBINE) {
 #pragma unroll
@@ -179,6 +193,15 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
                     const bool m = oc[i] < A[i];
                     ot[i * 32] = m ? A[i] : oc[i];
                     mt[i * 32] = m ? (uint8_t)ids.mine : (uint8_t)ids.first;
+                } else if (kThree) {
+                    // this direction (lowest id) first, then right (2), then left (3): strict <
+                    // keeps the lower id on ties, as the reference's Max chain does (:23-36)
+                    float best = A[i];
+                    uint8_t id = (uint8_t)ids.mine;
+                    if (best < oc[i]) { best = oc[i]; id = 2; }
+                    if (best < o3[i]) { best = o3[i]; id = 3; }
+                    ot[i * 32] = best;
+                    mt[i * 32] = id;
                 } else {
                     const bool m = oc[i] < A[i] || (oc[i] == A[i] && ids.mine < (int)mc[i]);
                     ot[i * 32] = m ? A[i] : oc[i];
@@ -197,6 +220,131 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
         named_barrier(1, NW * 32);
 #pragma unroll
         for (int i = 0; i < K; i++) P[i] = A[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// horizontal scans (right / left) in the STANDARD layout, no transposes.
+// A CTA owns 32 image rows of one slice; lane = row, warp = depth chunk.  TMA boxes of
+// (4 columns x 32 rows x D planes) land as [d][row][4] in shared memory, so every thread
+// fetches ITS four consecutive scan steps with one conflict-free 16-byte access, walks them
+// in registers (exchange + consumer barrier per step as in the vertical kernel), writes the
+// four aggregates back in place with one 16-byte store, and the producer stores the box.
+// DIR 0 = right (columns ascending), 1 = left.  Output: the raw aggregate.
+// ---------------------------------------------------------------------------
+template <int K, int MAXW, int DIR, bool FULL>
+__global__ void __launch_bounds__(MAXW * 32 + 32)
+sga_tma_hraw_kernel(const __grid_constant__ TmaHrawMaps maps, int D, int W, int strips, int S)
+{
+    static_assert(K % 2 == 0, "depth parity must be a compile-time property");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
+    const int NW = (blockDim.x >> 5) - 1;
+    const long long s = blockIdx.x / strips;
+    const int strip = blockIdx.x - (int)(s * strips);
+    const int h0 = strip * 32;
+    const int xbytes = D * 512, stage_bytes = xbytes + 2560;      // [D][32][4] + [5][32][4] floats
+    const int plane = NW * 32;
+    float *ex = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes + 2 * 3 * plane * 4);
+    uint64_t *done = full + S;
+    const int c2x = (int)(s * D), c2g = (int)(s * 5);
+    const int nb = W / 4;                                         // boxes along the scan
+
+    if (tid == 0) {
+        for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&done[i], NW * 32); }
+        fence_mbarrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (j == NW) {                                        // ---------------- producer
+        if (lane == 0) {
+            const unsigned tx = xbytes + 2560;
+            auto col_of = [&](int b) { return 4 * (DIR == 0 ? b : nb - 1 - b); };
+            auto issue = [&](int b) {
+                const int st = b % S;
+                unsigned char *p = smem + (size_t)st * stage_bytes;
+                mbar_arrive_expect_tx(&full[st], tx);
+                tma_load_3d(p, &maps.x, &full[st], col_of(b), h0, c2x);
+                tma_load_3d(p + xbytes, &maps.g, &full[st], col_of(b), h0, c2g);
+            };
+            for (int b = 0; b < S && b < nb; b++) issue(b);
+            for (int b = 0; b < nb; b++) {
+                const int st = b % S;
+                mbar_wait(&done[st], (b / S) & 1);
+                tma_store_3d(&maps.out, smem + (size_t)st * stage_bytes, col_of(b), h0, c2x);
+                tma_commit();
+                if (b + S < nb) {
+                    tma_wait_read_all();
+                    issue(b + S);
+                }
+            }
+            tma_wait_all();
+        }
+        return;
+    }
+
+    // ---------------- consumers
+    const int d0 = K * j;
+    const int toff = (d0 * 32 + lane) * 16;               // bytes: this thread's first 16-byte cell
+    float P[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) P[i] = 0.f;
+
+    for (int b = 0; b < nb; b++) {
+        const int st = b % S;
+        unsigned char *p = smem + (size_t)st * stage_bytes;
+        mbar_wait(&full[st], (b / S) & 1);
+        float4 *xt = reinterpret_cast<float4 *>(p + toff);
+        const float4 *gt = reinterpret_cast<const float4 *>(p + xbytes) + lane;
+        float xq[K][4], gq[5][4];
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            const float4 v = (FULL || d0 + i < D) ? xt[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+            xq[i][0] = v.x; xq[i][1] = v.y; xq[i][2] = v.z; xq[i][3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float4 v = gt[k * 32];
+            gq[k][0] = v.x; gq[k][1] = v.y; gq[k][2] = v.z; gq[k][3] = v.w;
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int q = (DIR == 0) ? qq : 3 - qq;       // compile-time after unrolling
+            const int t = b * 4 + qq;                     // scan step
+            float xc[K], w[5], A[K];
+#pragma unroll
+            for (int i = 0; i < K; i++) xc[i] = xq[i][q];
+#pragma unroll
+            for (int k = 0; k < 5; k++) w[k] = gq[k][q];
+            if (t == 0) {
+                sga_first_step<K>(xc, w, A);
+            } else {
+                const float *eb = ex + ((t - 1) & 1) * 3 * plane;
+                const float up = (j > 0) ? eb[plane + (j - 1) * 32 + lane] : 0.f;
+                const float dn = (j + 1 < NW) ? eb[(j + 1) * 32 + lane] : 0.f;
+                const float *mx = eb + 2 * plane + lane;
+                float pmax = mx[0];
+                for (int jj = 1; jj < NW; jj++) pmax = fmaxf(pmax, mx[jj * 32]);
+                sga_next_step<K, FULL>(P, xc, w, up, dn, pmax, d0, D, A);
+            }
+            {
+                float *wb = ex + (t & 1) * 3 * plane + j * 32 + lane;
+                wb[0] = A[0];
+                wb[plane] = A[K - 1];
+                wb[2 * plane] = FULL ? chunk_max<K>(A, 0, K) : chunk_max<K>(A, d0, D);
+            }
+#pragma unroll
+            for (int i = 0; i < K; i++) { P[i] = A[i]; xq[i][q] = A[i]; }
+            named_barrier(1, NW * 32);
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if (FULL || d0 + i < D) xt[i * 32] = make_float4(xq[i][0], xq[i][1], xq[i][2], xq[i][3]);
+        fence_proxy_async();
+        mbar_arrive(&done[st]);
     }
 }
 

@@ -19,7 +19,7 @@
 
 namespace ganet {
 
-enum { VMODE_FIRST = 0, VMODE_SECOND = 1, VMODE_COMBINE = 2, VMODE_RAW = 3 };
+enum { VMODE_FIRST = 0, VMODE_SECOND = 1, VMODE_COMBINE = 2, VMODE_RAW = 3, VMODE_FIRST3 = 4 };
 
 struct MaskIds { int first, mine; };   // direction ids written to the mask
 

@@ -108,10 +108,10 @@ static inline PFN_encodeTiled get_encode_tiled()
 }
 
 // A (rows x H x W) volume of `elem` bytes per element seen as a 3-D tensor
-// (dim0 = W contiguous, dim1 = H, dim2 = planes); box = (box_w, 1, box_planes).
+// (dim0 = W contiguous, dim1 = H, dim2 = planes); box = (box_w, box_h, box_planes).
 // Returns false if the shape violates a TMA constraint (caller falls back).
 static inline bool make_plane_map(CUtensorMap *map, const void *base, int elem, long long planes, int H,
-                                  int W, int box_w, int box_planes)
+                                  int W, int box_w, int box_planes, int box_h = 1)
 {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
@@ -120,7 +120,7 @@ static inline bool make_plane_map(CUtensorMap *map, const void *base, int elem, 
         return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)W * elem, (cuuint64_t)W * H * elem};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, 1u, (cuuint32_t)box_planes};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_planes};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                      const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
