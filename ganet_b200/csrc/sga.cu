@@ -492,6 +492,17 @@ static bool tma_enabled()
     return v != 0;
 }
 
+// L2 evict-first hints on the TMA traffic.  Measured on B200 at 1x32x192x240x624: WORSE
+// (forward 12.6 -> 15.1 ms, backward 28.1 -> 29.2 ms) -- neighbouring strips and consecutive
+// passes do profit from L2 -- so the hint is off unless GANET_L2_HINT=1 asks for it.
+static int stream_hint(long long n_slices, int D, int H, int W)
+{
+    (void)n_slices; (void)D; (void)H; (void)W;
+    static int forced = -2;
+    if (forced == -2) { const char *e = getenv("GANET_L2_HINT"); forced = e ? atoi(e) : 0; }
+    return forced > 0;
+}
+
 template <int MODE>
 static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, uint8_t *mask, int dir,
                           MaskIds ids, int D, int H, int W, long long n_slices, cudaStream_t st,
@@ -535,7 +546,8 @@ static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, ui
         auto k = full ? kf : kp;                                                               \
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
-        k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, dir, ids, D, H, strips, S);   \
+        k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, dir, ids, D, H, strips, S,    \
+                                                           stream_hint(n_slices, D, H, W));    \
     } else
     GANET_VERT_CFGS(X) { return kNotApplicable; }
 #undef X
@@ -575,7 +587,8 @@ static int launch_tma_bwd(VCfg c, const float *x, const float *g, const float *a
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
         k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, gi, gg, dir, mask_id,         \
-                                                           accumulate, D, H, W, strips, S);    \
+                                                           accumulate, D, H, W, strips, S,     \
+                                                           stream_hint(n_slices, D, H, W));    \
     } else
     GANET_VERT_CFGS(X) { return kNotApplicable; }
 #undef X

@@ -69,7 +69,7 @@ __host__ __device__ inline BwdPlan bwd_plan(int D)
 template <int K, int MAXW, int MODE, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32 + 32)
 sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids, int D, int H,
-                   int strips, int S)
+                   int strips, int S, int stream_hint)
 {
     static_assert(K % 2 == 0, "depth parity must be a compile-time property");
     constexpr bool kThree = (MODE == VMODE_FIRST3);       // merge down with the two horizontal aggregates
@@ -96,6 +96,15 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
 
     if (j == NW) {                                        // ---------------- producer
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            auto tma_load_3d = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+                if (stream_hint) ganet::tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
+                else ganet::tma_load_3d(dst, m, bar, c0, c1, c2);
+            };
+            auto tma_store_3d = [&](const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+                if (stream_hint) ganet::tma_store_3d_hint(m, src, c0, c1, c2, pol);
+                else ganet::tma_store_3d(m, src, c0, c1, c2);
+            };
             const unsigned tx = D * 128 + 640 + (kCombine ? D * 128 : 0) + (MODE == VMODE_COMBINE ? D * 32 : 0) +
                                 (kThree ? D * 128 : 0);
             auto issue = [&](int t) {
@@ -356,7 +365,8 @@ sga_tma_hraw_kernel(const __grid_constant__ TmaHrawMaps maps, int D, int W, int 
 template <int K, int MAXW, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32 + 32)
 sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old, float *__restrict__ gg,
-                   int dir, int mask_id, int accumulate, int D, int H, int W, int strips, int S)
+                   int dir, int mask_id, int accumulate, int D, int H, int W, int strips, int S,
+                   int stream_hint)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
@@ -382,6 +392,15 @@ sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old,
     // iteration `it` handles scan position t = H-1-it, image row h(t)
     if (j == NW) {                                        // ---------------- producer
         if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            auto tma_load_3d = [&](void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+                if (stream_hint) ganet::tma_load_3d_hint(dst, m, bar, c0, c1, c2, pol);
+                else ganet::tma_load_3d(dst, m, bar, c0, c1, c2);
+            };
+            auto tma_store_3d = [&](const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+                if (stream_hint) ganet::tma_store_3d_hint(m, src, c0, c1, c2, pol);
+                else ganet::tma_store_3d(m, src, c0, c1, c2);
+            };
             auto row_of = [&](int t) { return (dir == 0) ? t : H - 1 - t; };
             auto issue = [&](int it) {
                 const int st = it % S;

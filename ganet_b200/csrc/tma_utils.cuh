@@ -79,6 +79,34 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
         : "memory");
 }
 
+// streaming variants: L2 evict-first policy (the volumes are far larger than L2 and every
+// tile is touched once per pass)
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                                 int c1, int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *map, const void *src, int c0, int c1,
+                                                  int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

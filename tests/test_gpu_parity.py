@@ -172,15 +172,16 @@ def test_tma_and_ldg_kernels_agree_bitwise(ops):
         "print(h.hexdigest())"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     digests = []
-    for no_tma in ("", "1"):
+    # default (TMA + transpose-free forward for small calls), transposed TMA path, plain LDG kernels
+    for knobs in ({}, {"GANET_NO_DIRECT": "1"}, {"GANET_NO_TMA": "1"}):
         env = dict(os.environ)
-        env.pop("GANET_NO_TMA", None)
-        if no_tma:
-            env["GANET_NO_TMA"] = "1"
+        for k in ("GANET_NO_TMA", "GANET_NO_DIRECT", "GANET_FORCE_DIRECT"):
+            env.pop(k, None)
+        env.update(knobs)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr[-2000:]
         digests.append(r.stdout.strip().splitlines()[-1])
-    assert digests[0] == digests[1]
+    assert digests[0] == digests[1] == digests[2]
 
 
 def test_sga_ties_and_constant_input(ops):
