@@ -3,7 +3,10 @@
 launch list of scripts/one_pass.py into the per-kernel table committed under profiles/ and
 into profiles/traffic.json (DRAM bytes of the dominant op, read by bench.py).
 
-    python scripts/summarize_ncu.py gpurun_out/launches.csv profiles/r01_launches_per_kernel.txt [reps]
+    python scripts/summarize_ncu.py gpurun_out/launches.csv profiles/r01_launches_per_kernel.txt [per_rep]
+
+per_rep = launches of one repetition of scripts/one_pass.py (9 SGA forward + 16 SGA backward
++ 6 LGA2 = 31); the LAST repetition in the list is summarised.
 """
 import collections
 import csv
@@ -18,7 +21,7 @@ T = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecon
 
 def main():
     src, dst = sys.argv[1], sys.argv[2]
-    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    per_rep = int(sys.argv[3]) if len(sys.argv) > 3 else 31
     voxels = int(sys.argv[4]) if len(sys.argv) > 4 else 32 * 192 * 240 * 624
     lines = [l for l in open(src) if not l.startswith("==")]
     per = collections.OrderedDict()
@@ -27,9 +30,8 @@ def main():
         per.setdefault(k, {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * \
             (T.get(r["Metric Unit"], None) if r["Metric Name"].startswith("gpu__time") else F[r["Metric Unit"]])
     items = list(per.items())
-    n = len(items) // reps
-    last = items[-n:]                       # the last repetition (warm)
-    out = ["# ncu launch list of `python scripts/one_pass.py` (last of %d repetitions), one 920M-voxel sample" % reps,
+    last = items[-per_rep:]                 # the last repetition (warm)
+    out = ["# ncu launch list of `python scripts/one_pass.py`: the %d launches of its last repetition, one 920M-voxel sample" % per_rep,
            "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes",
            "%-4s %-58s %9s %9s %9s %8s" % ("id", "kernel", "ms", "rd GB", "wr GB", "GB/s")]
     tot = collections.Counter()
