@@ -349,6 +349,33 @@ def test_non_default_stream_and_threads(ops):
         assert np.array_equal(results[i][0], oo) and np.array_equal(results[i][1], om)
 
 
+def test_cuda_graph_capture_and_replay(ops):
+    """Every launch goes to the current stream and nothing synchronises, so a forward +
+    backward can be captured in a CUDA graph and replayed on new data (the reference's
+    synchronous cudaMemcpy calls on the legacy stream cannot)."""
+    shape = (1, 2, 24, 32, 48)
+    x, g, go = sga_inputs(shape, seed=21)
+    xs, gs, gos = cu(x), [cu(a) for a in g], cu(go)
+    ops.sga_forward(xs, *gs)                       # warm-up outside capture (allocator, tensor maps)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, mask = ops.sga_forward(xs, *gs)
+        gi, gg = ops.sga_backward(xs, *gs, mask, gos)
+    x2, g2, go2 = sga_inputs(shape, seed=22)
+    xs.copy_(cu(x2)); gos.copy_(cu(go2))
+    for dst, src in zip(gs, g2):
+        dst.copy_(cu(src))
+    graph.replay()
+    torch.cuda.synchronize()
+    oo, om = oracle.sga_forward(x2, *g2, fused=True)
+    ogi, ogg, _ = oracle.sga_backward(x2, *g2, om, go2, fused=True)
+    assert np.array_equal(npy(out), oo) and np.array_equal(npy(mask), om)
+    assert_close(npy(gi), ogi, RTOL, "gradInput")
+    for d in range(4):
+        assert_close(npy(gg[d]), ogg[d], RTOL, "guidance grad")
+
+
 @needs_ref
 def test_legacy_native_surface_matches_reference_extension():
     """ganet_b200.legacy_native honours the reference's buffer contract
