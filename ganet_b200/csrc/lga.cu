@@ -48,6 +48,43 @@ __device__ __forceinline__ void lga_taps(int h, int w, int H, int W, bool (&ok)[
         }
 }
 
+// the (2R+1)^2 neighbourhood of one plane.  Interior pixels: one pointer per filter row and
+// compile-time column offsets (LDG [R + imm]); rebuilding a 64-bit address from a runtime
+// offset for each of the 25 loads cost ~4 integer instructions per load.
+template <int R>
+__device__ __forceinline__ void lga_load_plane(const float *p, int W, bool interior,
+                                               const int (&noff)[LgaGeom<R>::P2],
+                                               float (&v)[LgaGeom<R>::P2])
+{
+    constexpr int WS = LgaGeom<R>::WS;
+    if (interior) {
+#pragma unroll
+        for (int r = -R; r <= R; r++) {
+            const float *row = p + r * W;
+#pragma unroll
+            for (int c = -R; c <= R; c++) v[(r + R) * WS + (c + R)] = ld_nc(row + c);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < LgaGeom<R>::P2; t++) v[t] = ld_nc(p + noff[t]);
+    }
+}
+
+// The plane walk has no register room for a software pipeline (75 tap weights live in
+// registers), so the rows of a plane a few steps ahead are pulled towards L1 instead.
+constexpr int kLgaPrefetch = 3;
+template <int R>
+__device__ __forceinline__ void lga_prefetch_plane(const float *p, int W, bool interior)
+{
+    if (interior) {
+#pragma unroll
+        for (int r = -R; r <= R; r++)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + r * W));
+    } else {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+}
+
 // ---- forward ---------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kLgaThreads)
@@ -69,6 +106,7 @@ lga_fwd_kernel(const float *__restrict__ x, const float *__restrict__ f, float *
     bool ok[P2];
     int noff[P2];
     lga_taps<R>(h, w, H, W, ok, noff);
+    const bool interior = (h >= R) && (h + R < H) && (w >= R) && (w + R < W);
     float wz[F];                 // tap weights, 0 where (r,c) leaves the image
     float cval[3] = {0.f, 0.f, 0.f};   // per depth tap: sum of the in-image weights
     float coob = 0.f;            // sum of all out-of-image weights (all three depth taps)
@@ -88,14 +126,26 @@ lga_fwd_kernel(const float *__restrict__ x, const float *__restrict__ f, float *
     for (int dp = max(dbeg - 1, 0); dp < min(dend + 1, D); dp++) {
         const float *xp = xb + (long long)dp * HW;
         const float ctr = ld_nc(xp);
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f;      // contributions of this plane to y[dp+1], y[dp], y[dp-1]
+        // contributions of this plane to y[dp+1], y[dp], y[dp-1]; one partial sum per filter
+        // row so that 3*(2R+1) FMA chains are in flight instead of 3 (latency-bound at 8 warps/SM)
+        float q0[2 * R + 1], q1[2 * R + 1], q2[2 * R + 1];
+        float v[P2];
+        if (dp + kLgaPrefetch < D) lga_prefetch_plane<R>(xp + (long long)kLgaPrefetch * HW, W, interior);
+        lga_load_plane<R>(xp, W, interior, noff, v);
 #pragma unroll
-        for (int t = 0; t < P2; t++) {
-            const float v = ld_nc(xp + noff[t]);
-            n0 = fmaf(v, wz[0 * P2 + t], n0);    // depth tap -1 of output dp+1
-            n1 = fmaf(v, wz[1 * P2 + t], n1);    // depth tap  0 of output dp
-            n2 = fmaf(v, wz[2 * P2 + t], n2);    // depth tap +1 of output dp-1
+        for (int r = 0; r < 2 * R + 1; r++) {
+            q0[r] = 0.f; q1[r] = 0.f; q2[r] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2 * R + 1; c++) {
+                const int t = r * (2 * R + 1) + c;
+                q0[r] = fmaf(v[t], wz[0 * P2 + t], q0[r]);    // depth tap -1 of output dp+1
+                q1[r] = fmaf(v[t], wz[1 * P2 + t], q1[r]);    // depth tap  0 of output dp
+                q2[r] = fmaf(v[t], wz[2 * P2 + t], q2[r]);    // depth tap +1 of output dp-1
+            }
         }
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2 * R + 1; r++) { n0 += q0[r]; n1 += q1[r]; n2 += q2[r]; }
         a0 += n2; a1 += n1; a2 += n0;
         // centre-fallback terms of output dp (its own centre): out-of-image taps always,
         // plus the whole -1 / +1 depth tap at the volume faces
@@ -133,6 +183,7 @@ lga_bwd_filter_kernel(const float *__restrict__ x, const float *__restrict__ go,
     bool ok[P2];
     int noff[P2];
     lga_taps<R>(h, w, H, W, ok, noff);
+    const bool interior = (h >= R) && (h + R < H) && (w >= R) && (w + R < W);
     float acc[F];
 #pragma unroll
     for (int l = 0; l < F; l++) acc[l] = 0.f;
@@ -148,12 +199,17 @@ lga_bwd_filter_kernel(const float *__restrict__ x, const float *__restrict__ go,
         sgc = fmaf(gc, ctr, sgc);
         if (dp == 0) e_first = gc * ctr;
         if (dp == D - 1) e_last = gc * ctr;
+        float v[P2];
+        if (dp + kLgaPrefetch < D) {
+            lga_prefetch_plane<R>(xp + (long long)kLgaPrefetch * HW, W, interior);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(gb + (long long)(dp + kLgaPrefetch) * HW));
+        }
+        lga_load_plane<R>(xp, W, interior, noff, v);
 #pragma unroll
         for (int t = 0; t < P2; t++) {
-            const float v = ld_nc(xp + noff[t]);
-            acc[0 * P2 + t] = fmaf(gp, v, acc[0 * P2 + t]);
-            acc[1 * P2 + t] = fmaf(gc, v, acc[1 * P2 + t]);
-            acc[2 * P2 + t] = fmaf(gm, v, acc[2 * P2 + t]);
+            acc[0 * P2 + t] = fmaf(gp, v[t], acc[0 * P2 + t]);
+            acc[1 * P2 + t] = fmaf(gc, v[t], acc[1 * P2 + t]);
+            acc[2 * P2 + t] = fmaf(gm, v[t], acc[2 * P2 + t]);
         }
         gm = gc; gc = gp;
     }
@@ -193,6 +249,7 @@ lga_bwd_data_kernel(const float *__restrict__ f, const float *__restrict__ go,
     bool ok[P2];
     int noff[P2];
     lga_taps<R>(h, w, H, W, ok, noff);
+    const bool interior = (h >= R) && (h + R < H) && (w >= R) && (w + R < W);
     float wn[F];                 // mirrored weight of the neighbour pixel, 0 outside the image
     float cval[3] = {0.f, 0.f, 0.f};   // this pixel's own in-image weights per depth tap
     float coob = 0.f;                  // this pixel's own out-of-image weights
@@ -215,14 +272,24 @@ lga_bwd_data_kernel(const float *__restrict__ f, const float *__restrict__ go,
     for (int dp = max(dbeg - 1, 0); dp < min(dend + 1, D); dp++) {
         const float *gp = gb + (long long)dp * HW;
         const float ctr = ld_nc(gp);
+        float q0[2 * R + 1], q1[2 * R + 1], q2[2 * R + 1];
+        float v[P2];
+        if (dp + kLgaPrefetch < D) lga_prefetch_plane<R>(gp + (long long)kLgaPrefetch * HW, W, interior);
+        lga_load_plane<R>(gp, W, interior, noff, v);
+#pragma unroll
+        for (int r = 0; r < 2 * R + 1; r++) {
+            q0[r] = 0.f; q1[r] = 0.f; q2[r] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2 * R + 1; c++) {
+                const int t = r * (2 * R + 1) + c;
+                q0[r] = fmaf(v[t], wn[0 * P2 + t], q0[r]);    // go plane dp is the dd=-1 neighbour of output dp+1
+                q1[r] = fmaf(v[t], wn[1 * P2 + t], q1[r]);
+                q2[r] = fmaf(v[t], wn[2 * P2 + t], q2[r]);    // ... and the dd=+1 neighbour of output dp-1
+            }
+        }
         float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < P2; t++) {
-            const float v = ld_nc(gp + noff[t]);
-            n0 = fmaf(v, wn[0 * P2 + t], n0);    // go plane dp is the dd=-1 neighbour of output dp+1
-            n1 = fmaf(v, wn[1 * P2 + t], n1);
-            n2 = fmaf(v, wn[2 * P2 + t], n2);    // ... and the dd=+1 neighbour of output dp-1
-        }
+        for (int r = 0; r < 2 * R + 1; r++) { n0 += q0[r]; n1 += q1[r]; n2 += q2[r]; }
         a0 += n2; a1 += n1; a2 += n0;
         float fb_w = coob;
         if (dp == 0) fb_w += cval[0];
