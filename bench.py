@@ -408,6 +408,29 @@ def run_ours(a):
     calls = a.steps * -(-len(mine) // cs)
     launches = calls * (9 + 16 + 2 + 4)
 
+    # ---- roofline of the single hottest kernel family, timed alone ------------------
+    # one directional aggregate = ONE launch of the TMA scan kernel in RAW mode: reads x and the
+    # guidance once, writes the aggregate once (8 + 20/D algorithmic bytes per voxel)
+    kern = None
+    if len(mine) > 0:
+        s1 = slice(0, min(cs, len(mine)))
+        vox = x[s1].numel()
+        ops.sga_direction(x[s1], g[0][s1], 0)
+        torch.cuda.synchronize()
+        k0, k1 = ev(), ev()
+        reps = 5
+        k0.record()
+        for r in range(reps):
+            ops.sga_direction(x[s1], g[r % 2][s1], r % 2)       # down / up alternate
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        kgbs = (8.0 + 20.0 / D) * vox / (kms * 1e-3) / 1e9
+        kern = {"kernel": "sga_tma_fwd_kernel, RAW mode (one scan direction, one launch)",
+                "bound": "hbm", "achieved": kgbs, "peak": peak, "unit": "GB/s", "frac": kgbs / peak,
+                "ms_per_launch": kms, "voxels_per_launch": vox,
+                "algorithmic_bytes_per_voxel": 8.0 + 20.0 / D}
+
     # ---- end to end through the public modules, from pinned host buffers ---------
     e2e = None
     if not a.no_e2e and len(mine) > 0:
@@ -431,6 +454,7 @@ def run_ours(a):
                          "frac": sga_gbs / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": sga_bytes_per_voxel(D),
                          "traffic": traffic},
+            "roofline_hottest_kernel": kern,
             "phases_ms_per_step": {"sga_fwd": ph[0] / a.steps, "sga_bwd": ph[1] / a.steps,
                                    "lga2_fwd": ph[2] / a.steps, "lga2_bwd": ph[3] / a.steps},
         }
