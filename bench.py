@@ -340,14 +340,23 @@ def run_ours(a):
     phase_events = []
 
     cs = max(1, min(a.chunk, max(1, len(mine))))
+    keep_flag = [None]
 
     def one_sample(i, record):
         s = slice(i, min(i + cs, len(mine)))
         e = [ev() for _ in range(5)] if record else None
         if record: e[0].record()
-        out, mask = ops.sga_forward(x[s], g[0][s], g[1][s], g[2][s], g[3][s])
+        # forward keeps the four aggregates for backward when the device has room
+        # (ops.keep_aggregates_policy: the same rule SgaFunction applies under autograd)
+        agg = None
+        if keep_flag[0] is None:
+            keep_flag[0] = ops.keep_aggregates_policy(x[s], True)
+        if keep_flag[0]:
+            out, mask, agg = ops.sga_forward(x[s], g[0][s], g[1][s], g[2][s], g[3][s], keep_aggregates=True)
+        else:
+            out, mask = ops.sga_forward(x[s], g[0][s], g[1][s], g[2][s], g[3][s])
         if record: e[1].record()
-        gi, gg = ops.sga_backward(x[s], g[0][s], g[1][s], g[2][s], g[3][s], mask, go[s])
+        gi, gg = ops.sga_backward(x[s], g[0][s], g[1][s], g[2][s], g[3][s], mask, go[s], aggregates=agg)
         if record: e[2].record()
         y1 = ops.lga_forward(xl[s], fl[s], 2)
         y = ops.lga_forward(y1, fl[s], 2)
@@ -403,10 +412,11 @@ def run_ours(a):
     # launches of OUR kernels in the timed region: SGA fwd 4, SGA bwd 8 per workspace
     # chunk, LGA2 fwd 2, LGA2 bwd 4 -- per sample per step
     # launches per native call when the workspace holds the whole call in one chunk:
-    # SGA fwd 3 + 2 + 2 + 2 = 9 (transposes, 2 horizontal, 2 back-transposes, 2 vertical),
-    # SGA bwd 4 + 3 + 2*(1+1+1+1) + 1 = 16, LGA2 fwd 2, LGA2 bwd 4
+    # SGA fwd 9 (3 transposes, 2 horizontal scans, 2 back-transposes, 2 vertical scans) or, keeping
+    # the aggregates, 10 (4 raw scans, 5 transposes, 1 merge); SGA bwd 16, or 12 without the four
+    # recompute scans; LGA2 fwd 2, LGA2 bwd 4
     calls = a.steps * -(-len(mine) // cs)
-    launches = calls * (9 + 16 + 2 + 4)
+    launches = calls * ((10 + 12 if keep_flag[0] else 9 + 16) + 2 + 4)
 
     # ---- roofline of the single hottest kernel family, timed alone ------------------
     # one directional aggregate = ONE launch of the TMA scan kernel in RAW mode: reads x and the
@@ -447,9 +457,10 @@ def run_ours(a):
                                    "batch sharded over ranks, %d samples per call"
                                    % (B, C, D, H, W, B, D, H, W, cs),
                        "global_batch": B, "parallelism": "batch-shard x%d, no data-path collective" % world,
-                       "l2": "inputs larger than L2 (3.7 GB per sample, distinct per sample)"},
+                       "l2": "inputs larger than L2 (3.7 GB per sample, distinct per sample)",
+                       "aggregates_kept_for_backward": bool(keep_flag[0])},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (9 + 16 launches per call: scans + H<->W transposes)",
+            "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (all launches of the call: scans + H<->W transposes + merge)",
                          "achieved": sga_gbs, "peak": peak, "unit": "GB/s",
                          "frac": sga_gbs / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": sga_bytes_per_voxel(D),

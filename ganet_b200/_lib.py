@@ -21,12 +21,12 @@ _sz = ctypes.c_size_t
 _SIGNATURES = {
     "ganet_abi_version": (_int, []),
     "ganet_error_string": (ctypes.c_char_p, [_int]),
-    "ganet_sga_forward": (_int, [_vp] * 8 + [_sz] + [_i64] * 5 + [_vp]),
+    "ganet_sga_forward": (_int, [_vp] * 9 + [_sz] + [_i64] * 5 + [_vp]),
     "ganet_sga_forward_workspace_min": (_sz, [_i64] * 5),
     "ganet_sga_forward_workspace_best": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_min": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_best": (_sz, [_i64] * 5),
-    "ganet_sga_backward": (_int, [_vp] * 14 + [_sz] + [_i64] * 5 + [_vp]),
+    "ganet_sga_backward": (_int, [_vp] * 15 + [_sz] + [_i64] * 5 + [_vp]),
     "ganet_sga_direction": (_int, [_vp] * 3 + [_int] + [_i64] * 5 + [_vp]),
     "ganet_lga_forward": (_int, [_vp] * 3 + [_i64] * 4 + [_int, _vp]),
     "ganet_lga_backward": (_int, [_vp] * 5 + [_int] + [_i64] * 4 + [_int, _vp]),
@@ -58,7 +58,7 @@ def lib():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.ganet_abi_version() != 1:
+        if handle.ganet_abi_version() != 2:
             raise GanetNativeError("ganet_b200: ABI version mismatch")
         _lib = handle
     return _lib

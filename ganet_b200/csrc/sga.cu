@@ -683,13 +683,14 @@ using namespace ganet;
 // ---- workspace carving ------------------------------------------------------------
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-struct FwdWs { size_t xT, outT, maskT, gT2, gT3, total; };
-static FwdWs fwd_ws(long long n, long long S, long long HW)
+struct FwdWs { size_t xT, outT, maskT, t3, gT2, gT3, total; };
+static FwdWs fwd_ws(long long n, long long S, long long HW, bool keep = false)
 {
     FwdWs w; size_t o = 0;
     w.xT = o;    o += align_up((size_t)n * S * 4);
-    w.outT = o;  o += align_up((size_t)n * S * 4);
-    w.maskT = o; o += align_up((size_t)n * S);
+    w.outT = o;  o += align_up((size_t)n * S * 4);     // keep: `right` aggregate back in the standard layout
+    w.maskT = o; o += keep ? 0 : align_up((size_t)n * S);
+    w.t3 = o;    o += keep ? align_up((size_t)n * S * 4) : 0;   // keep: `left` aggregate, standard layout
     w.gT2 = o;   o += align_up((size_t)n * 5 * HW * 4);
     w.gT3 = o;   o += align_up((size_t)n * 5 * HW * 4);
     w.total = o;
@@ -697,10 +698,10 @@ static FwdWs fwd_ws(long long n, long long S, long long HW)
 }
 
 struct BwdWs { size_t a, xT, goT, maskT, giT, gT, ggT, total; };
-static BwdWs bwd_ws(long long n, long long S, long long HW)
+static BwdWs bwd_ws(long long n, long long S, long long HW, bool kept = false)
 {
     BwdWs w; size_t o = 0;
-    w.a = o;     o += align_up((size_t)n * S * 4);
+    w.a = o;     o += kept ? 0 : align_up((size_t)n * S * 4);    // kept aggregates: no recompute scratch
     w.xT = o;    o += align_up((size_t)n * S * 4);
     w.goT = o;   o += align_up((size_t)n * S * 4);
     w.maskT = o; o += align_up((size_t)n * S);
@@ -727,11 +728,13 @@ static long long fit_slices(F sizer, size_t bytes, long long ns)
 GANET_API size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
     (void)N; (void)C;
-    return fwd_ws(1, D * H * W, H * W).total;
+    const size_t a = fwd_ws(1, D * H * W, H * W, false).total, b = fwd_ws(1, D * H * W, H * W, true).total;
+    return a > b ? a : b;          // one size serves both forward variants
 }
 GANET_API size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
-    return fwd_ws(N * C, D * H * W, H * W).total;
+    const size_t a = fwd_ws(N * C, D * H * W, H * W, false).total, b = fwd_ws(N * C, D * H * W, H * W, true).total;
+    return a > b ? a : b;
 }
 GANET_API size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
@@ -760,8 +763,9 @@ static int sga_forward_lines(const float *x, const float *const g[4], float *out
 
 GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float *g_up,
                                 const float *g_right, const float *g_left, float *out,
-                                uint8_t *mask, void *workspace, size_t workspace_bytes, int64_t N,
-                                int64_t C, int64_t D, int64_t H, int64_t W, ganet_stream_t stream)
+                                uint8_t *mask, float *aggregates, void *workspace,
+                                size_t workspace_bytes, int64_t N, int64_t C, int64_t D, int64_t H,
+                                int64_t W, ganet_stream_t stream)
 {
     if (!x || !g_down || !g_up || !g_right || !g_left || !out || !mask) return GANET_EINVAL;
     int rc = check_dims(N, C, D, H, W);
@@ -770,16 +774,41 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
     const long long S = D * H * W, HW = H * W, ns = N * C;
     const float *g[4] = {g_down, g_up, g_right, g_left};
     VCfg vc;
-    if (!pick_vert_cfg((int)D, &vc))
+    if (!pick_vert_cfg((int)D, &vc)) {
+        if (aggregates) return GANET_EUNSUPPORTED;       // D > 288: the generic path keeps nothing
         return sga_forward_lines(x, g, out, mask, (int)D, (int)H, (int)W, ns, st);
+    }
+    const bool keep = aggregates != nullptr;
     const long long chunk = workspace
-        ? fit_slices([&](long long n) { return fwd_ws(n, S, HW).total; }, workspace_bytes, ns) : 0;
+        ? fit_slices([&](long long n) { return fwd_ws(n, S, HW, keep).total; }, workspace_bytes, ns) : 0;
     if (chunk < 1) return GANET_EWORKSPACE;
     char *ws = (char *)workspace;
     const int iD = (int)D, iH = (int)H, iW = (int)W;
     for (long long s0 = 0; s0 < ns; s0 += chunk) {
         const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
-        const FwdWs w = fwd_ws(n, S, HW);
+        const FwdWs w = fwd_ws(n, S, HW, keep);
+        if (keep) {
+            // Memory-for-bandwidth variant: every direction's raw aggregate goes to the caller's
+            // buffer (down, up in the standard layout; right, left transposed -- the layouts
+            // backward consumes), one streaming kernel merges the four.  Backward then skips
+            // its four recompute passes.
+            float *xT = (float *)(ws + w.xT), *t2 = (float *)(ws + w.outT), *t3 = (float *)(ws + w.t3);
+            float *gT2 = (float *)(ws + w.gT2), *gT3 = (float *)(ws + w.gT3);
+            const float *xs = x + s0 * S;
+            float *A0 = aggregates + 0 * ns * S + s0 * S, *A1 = aggregates + 1 * ns * S + s0 * S;
+            float *A2T = aggregates + 2 * ns * S + s0 * S, *A3T = aggregates + 3 * ns * S + s0 * S;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_down + s0 * 5 * HW, A0, nullptr, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_up + s0 * 5 * HW, A1, nullptr, 1, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+            if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
+            if ((rc = launch_transpose<float, false>(g_right + s0 * 5 * HW, gT2, n * 5, iH, iW, st))) return rc;
+            if ((rc = launch_transpose<float, false>(g_left + s0 * 5 * HW, gT3, n * 5, iH, iW, st))) return rc;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT2, A2T, nullptr, 0, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
+            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT3, A3T, nullptr, 1, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
+            if ((rc = launch_transpose<float, false>(A2T, t2, n * D, iW, iH, st))) return rc;
+            if ((rc = launch_transpose<float, false>(A3T, t3, n * D, iW, iH, st))) return rc;
+            if ((rc = launch_merge4(A0, A1, t2, t3, out + s0 * S, mask + s0 * S, n * S, st))) return rc;
+            continue;
+        }
         float *xT = (float *)(ws + w.xT), *outT = (float *)(ws + w.outT);
         uint8_t *maskT = (uint8_t *)(ws + w.maskT);
         float *gT2 = (float *)(ws + w.gT2), *gT3 = (float *)(ws + w.gT3);
@@ -862,10 +891,11 @@ static int sga_backward_lines(const float *x, const float *const g[4], const uin
 
 GANET_API int ganet_sga_backward(const float *x, const float *g_down, const float *g_up,
                                  const float *g_right, const float *g_left, const uint8_t *mask,
-                                 const float *grad_out, float *grad_in, float *gg_down,
-                                 float *gg_up, float *gg_right, float *gg_left, int32_t *max_idx,
-                                 void *workspace, size_t workspace_bytes, int64_t N, int64_t C,
-                                 int64_t D, int64_t H, int64_t W, ganet_stream_t stream)
+                                 const float *aggregates, const float *grad_out, float *grad_in,
+                                 float *gg_down, float *gg_up, float *gg_right, float *gg_left,
+                                 int32_t *max_idx, void *workspace, size_t workspace_bytes,
+                                 int64_t N, int64_t C, int64_t D, int64_t H, int64_t W,
+                                 ganet_stream_t stream)
 {
     if (!x || !g_down || !g_up || !g_right || !g_left || !mask || !grad_out || !grad_in ||
         !gg_down || !gg_up || !gg_right || !gg_left || !workspace)
@@ -879,18 +909,20 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
     const int iD = (int)D, iH = (int)H, iW = (int)W;
     VCfg vc;
     if (!pick_vert_cfg(iD, &vc)) {
+        if (aggregates) return GANET_EUNSUPPORTED;       // the generic path recomputes
         const long long fit = (long long)(workspace_bytes / ((size_t)S * sizeof(float)));
         if (fit < 1) return GANET_EWORKSPACE;
         return sga_backward_lines(x, g, mask, grad_out, grad_in, gg, max_idx, (float *)workspace,
                                   fit < ns ? fit : ns, iD, iH, iW, ns, st);
     }
+    const bool kept = aggregates != nullptr;     // forward kept the four aggregates: no recompute
     const long long chunk =
-        fit_slices([&](long long n) { return bwd_ws(n, S, HW).total; }, workspace_bytes, ns);
+        fit_slices([&](long long n) { return bwd_ws(n, S, HW, kept).total; }, workspace_bytes, ns);
     if (chunk < 1) return GANET_EWORKSPACE;
     char *ws = (char *)workspace;
     for (long long s0 = 0; s0 < ns; s0 += chunk) {
         const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
-        const BwdWs w = bwd_ws(n, S, HW);
+        const BwdWs w = bwd_ws(n, S, HW, kept);
         float *a = (float *)(ws + w.a), *xT = (float *)(ws + w.xT), *goT = (float *)(ws + w.goT);
         float *giT = (float *)(ws + w.giT), *gT = (float *)(ws + w.gT), *ggT = (float *)(ws + w.ggT);
         uint8_t *maskT = (uint8_t *)(ws + w.maskT);
@@ -899,22 +931,26 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
         float *gis = grad_in + s0 * S;
         // vertical directions in place
         for (int dir = 0; dir < 2; dir++) {
-            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g[dir] + s0 * 5 * HW, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
-            if ((rc = run_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, a, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
+            const float *ak = kept ? aggregates + dir * ns * S + s0 * S : a;
+            if (!kept)
+                if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g[dir] + s0 * 5 * HW, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+            if ((rc = run_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, ak, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
         }
         // horizontal directions on the transposed slices
         if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(gos, goT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose_u8(ms, maskT, n * D, iH, iW, st))) return rc;
         for (int dir = 2; dir < 4; dir++) {
+            const float *ak = kept ? aggregates + dir * ns * S + s0 * S : a;
             if ((rc = launch_transpose<float, false>(g[dir] + s0 * 5 * HW, gT, n * 5, iH, iW, st))) return rc;
-            if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
+            if (!kept)
+                if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
             if (max_idx && dir == 2) {
                 dim3 grid((unsigned)((HW + 255) / 256), (unsigned)n);
-                max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(a, max_idx + s0 * HW, iD, iH, iW);
+                max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(ak, max_idx + s0 * HW, iD, iH, iW);
                 GANET_RETURN_IF_LAUNCH_FAILED();
             }
-            if ((rc = run_vert_bwd(vc, xT, gT, a, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
+            if ((rc = run_vert_bwd(vc, xT, gT, ak, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
             if ((rc = launch_transpose<float, false>(ggT, gg[dir] + s0 * 5 * HW, n * 5, iW, iH, st))) return rc;
         }
         if ((rc = launch_transpose<float, true>(giT, gis, n * D, iW, iH, st))) return rc;   // gi += giT^T

@@ -3,8 +3,9 @@ libs/GANet/functions/GANet.py (same class names, argument order and returned
 gradients), re-implemented over the C ABI.
 
 Differences from the reference, all deliberate:
-  * nothing is saved that backward can recompute: SgaFunction saves a 1-byte
-    direction mask instead of two fp32 volumes (functions/GANet.py:21);
+  * SgaFunction saves a 1-byte direction mask instead of two fp32 volumes
+    (functions/GANet.py:21) and, when memory allows (ops.keep_aggregates_policy), the four
+    directional aggregates, which lets backward skip its recompute passes;
   * backward never writes into its incoming gradOutput storage or into saved
     tensors (the reference does both, functions/GANet.py:197-200,
     GANet_kernel.cu:1064), so retain_graph / double use of a gradient works;
@@ -33,16 +34,25 @@ class SgaFunction(Function):
     @staticmethod
     def forward(ctx, input, g0, g1, g2, g3):
         _assert_contiguous(input, g0, g1, g2, g3)
-        output, mask = ops.sga_forward(input, g0, g1, g2, g3)
-        ctx.save_for_backward(input, g0, g1, g2, g3, mask)
+        needs_bwd = any(t.requires_grad for t in (input, g0, g1, g2, g3))
+        if ops.keep_aggregates_policy(input, needs_bwd):
+            # memory-for-bandwidth: keep the four directional aggregates (16 B/voxel) so that
+            # backward skips its recompute passes; ops.keep_aggregates_policy decides
+            output, mask, agg = ops.sga_forward(input, g0, g1, g2, g3, keep_aggregates=True)
+            ctx.save_for_backward(input, g0, g1, g2, g3, mask, agg)
+        else:
+            output, mask = ops.sga_forward(input, g0, g1, g2, g3)
+            ctx.save_for_backward(input, g0, g1, g2, g3, mask)
         return output
 
     @staticmethod
     def backward(ctx, gradOutput):
-        input, g0, g1, g2, g3, mask = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        input, g0, g1, g2, g3, mask = saved[:6]
+        agg = saved[6] if len(saved) > 6 else None
         gradOutput = gradOutput.contiguous()
         gradInput, (grad0, grad1, grad2, grad3) = ops.sga_backward(input, g0, g1, g2, g3, mask,
-                                                                   gradOutput)
+                                                                   gradOutput, aggregates=agg)
         return gradInput, grad0, grad1, grad2, grad3
 
 

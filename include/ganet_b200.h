@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GANET_B200_ABI_VERSION 1
+#define GANET_B200_ABI_VERSION 2
 
 typedef void *ganet_stream_t; /* cudaStream_t */
 
@@ -66,15 +66,23 @@ const char *ganet_error_string(int code);
  *       L1-normalised them over dim 2 (models/GANet_deep.py:265-268)
  *   mask   : (N, C, D, H, W) uint8, winning direction 0=down 1=up 2=right
  *       3=left, ties keep the lower id (GANet_kernel.cu:23-36)
+ *   aggregates : optional (may be NULL).  4 * N*C*D*H*W floats that receive the four
+ *       directional aggregates -- down, up as (N,C,D,H,W); right, left TRANSPOSED as
+ *       (N,C,D,W,H) -- for ganet_sga_backward, which then skips its four recompute
+ *       passes (-11 % DRAM traffic for forward+backward, +16 bytes per voxel of saved
+ *       state; the reference saves 8: temp_out and an fp32 mask, functions/GANet.py:21).
+ *       Needs D <= 288.
  *   workspace : device scratch (transposed copies for the horizontal scans),
  *       >= ganet_sga_forward_workspace_min bytes; the (n,c) slices are processed
  *       in chunks that fit, so any size between _min and _best works
- * Values of `out` and `mask` are bit-identical to the reference CUDA build.
+ * Values of `out` and `mask` are bit-identical to the reference CUDA build, with or
+ * without `aggregates`.
  */
 int ganet_sga_forward(const float *x, const float *g_down, const float *g_up,
                       const float *g_right, const float *g_left, float *out,
-                      uint8_t *mask, void *workspace, size_t workspace_bytes, int64_t N,
-                      int64_t C, int64_t D, int64_t H, int64_t W, ganet_stream_t stream);
+                      uint8_t *mask, float *aggregates, void *workspace,
+                      size_t workspace_bytes, int64_t N, int64_t C, int64_t D, int64_t H,
+                      int64_t W, ganet_stream_t stream);
 
 /* Bytes of scratch the SGA calls need at least (one (n,c) slice in flight) and
  * the size at which they run all slices in one chunk. */
@@ -88,6 +96,7 @@ size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_
  * GANet_kernel.cu:1000-1129).  Reproduces the reference's gradient, including
  * its first-scan-step quirks.
  *   grad_out, grad_in : (N, C, D, H, W);  gg_* : (N, C, 5, H, W), overwritten
+ *   aggregates : NULL, or the buffer ganet_sga_forward filled for the same inputs
  *   max_idx : optional (N, C, H, W) int32, depth arg-max of the `right`
  *       aggregate -- what the reference leaves in its max_idx buffer
  *       (GANet_kernel.cu:1119); may be NULL
@@ -96,10 +105,10 @@ size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_
  */
 int ganet_sga_backward(const float *x, const float *g_down, const float *g_up,
                        const float *g_right, const float *g_left, const uint8_t *mask,
-                       const float *grad_out, float *grad_in, float *gg_down,
-                       float *gg_up, float *gg_right, float *gg_left, int32_t *max_idx,
-                       void *workspace, size_t workspace_bytes, int64_t N, int64_t C,
-                       int64_t D, int64_t H, int64_t W, ganet_stream_t stream);
+                       const float *aggregates, const float *grad_out, float *grad_in,
+                       float *gg_down, float *gg_up, float *gg_right, float *gg_left,
+                       int32_t *max_idx, void *workspace, size_t workspace_bytes, int64_t N,
+                       int64_t C, int64_t D, int64_t H, int64_t W, ganet_stream_t stream);
 
 /* One directional aggregate without the max-combine (test / debug aid; the
  * reference exposes the `left` one as temp_out, functions/GANet.py:15,21).

@@ -44,6 +44,11 @@ def main():
     out, mask = ops.sga_forward(x, *g)
     ms = timeit(lambda: ops.sga_backward(x, *g, mask, go), a.iters)
     print("  sga_backward        %8.3f ms  %7.1f Gvox/s  algorithmic %.1f GB/s" % (ms, V / ms / 1e6, (13 + 160 / D) * V / ms / 1e6))
+    del out, mask
+    msf = timeit(lambda: ops.sga_forward(x, *g, keep_aggregates=True), a.iters)
+    out, mask, agg = ops.sga_forward(x, *g, keep_aggregates=True)
+    msb = timeit(lambda: ops.sga_backward(x, *g, mask, go, aggregates=agg), a.iters)
+    print("  kept aggregates: fwd %8.3f ms  bwd %8.3f ms  sum %8.3f ms" % (msf, msb, msf + msb))
     if a.lga:
         xl = torch.randn(N, D, H, W, device=dev)
         fl = F.normalize(torch.randn(N, 75, H, W, device=dev), p=1, dim=1)

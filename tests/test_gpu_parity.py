@@ -136,6 +136,44 @@ def test_sga_backward_workspace_chunking_is_invisible(ops):
     assert torch.equal(o1, out) and torch.equal(m1, mask)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 10, 7, 9), (1, 2, 24, 32, 48), (2, 2, 65, 32, 80), (1, 8, 48, 48, 96)])
+def test_kept_aggregates_give_identical_results(ops, shape):
+    """The memory-for-bandwidth variant (forward keeps the four aggregates, backward skips
+    its recompute passes) must not change a single bit, with any workspace chunking."""
+    x, g, go = sga_inputs(shape, seed=31 + sum(shape))
+    xt, gt, got = cu(x), [cu(a) for a in g], cu(go)
+    out, mask = ops.sga_forward(xt, *gt)
+    out2, mask2, agg = ops.sga_forward(xt, *gt, keep_aggregates=True)
+    assert torch.equal(out, out2) and torch.equal(mask, mask2)
+    out3, mask3, agg3 = ops.sga_forward(xt, *gt, keep_aggregates=True, workspace_bytes=1)
+    assert torch.equal(out, out3) and torch.equal(mask, mask3) and torch.equal(agg, agg3)
+    for d in (0, 1):
+        assert torch.equal(agg[d].view_as(xt), ops.sga_direction(xt, gt[d], d))
+    for d in (2, 3):
+        a = ops.sga_direction(xt, gt[d], d)
+        assert torch.equal(agg[d].view(*shape[:3], shape[4], shape[3]), a.transpose(3, 4).contiguous())
+    ref = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True)
+    for wsb in (None, 1):
+        got2 = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True, aggregates=agg, workspace_bytes=wsb)
+        assert torch.equal(ref[0], got2[0]) and torch.equal(ref[2], got2[2])
+        assert all(torch.equal(p, q) for p, q in zip(ref[1], got2[1]))
+
+
+def test_sga_module_keeps_aggregates_by_policy(monkeypatch):
+    from ganet_b200.modules import SGA
+    x, g, go = sga_inputs((1, 2, 8, 6, 7), seed=5)
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GANET_B200_KEEP_AGGREGATES", mode)
+        xt = cu(x).requires_grad_()
+        gt = [cu(a).requires_grad_() for a in g]
+        out = SGA()(xt, *gt)
+        assert len(out.grad_fn.saved_tensors) == (7 if mode == "1" else 6)
+        out.backward(cu(go))
+        grads[mode] = [xt.grad] + [t.grad for t in gt]
+    assert all(torch.equal(a, b) for a, b in zip(grads["0"], grads["1"]))
+
+
 def test_sga_against_golden_vectors(ops):
     z = np.load(os.path.join(GOLD, "sga_ref_cpu.npz"))
     for k in range(int(z["n"])):

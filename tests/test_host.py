@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(native_so):
     from ganet_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == names      # the Python binding covers the whole header
     handle.ganet_abi_version.restype = ctypes.c_int
-    assert handle.ganet_abi_version() == 1
+    assert handle.ganet_abi_version() == 2
     handle.ganet_error_string.restype = ctypes.c_char_p
     assert b"workspace" in handle.ganet_error_string(-3)
 
@@ -57,18 +57,20 @@ def test_argument_validation_without_gpu(native_so):
     L = _lib.lib()
     i64 = ctypes.c_int64
     sz = ctypes.c_size_t
-    assert L.ganet_sga_forward(None, None, None, None, None, None, None, None, sz(0),
+    assert L.ganet_sga_forward(None, None, None, None, None, None, None, None, None, sz(0),
                                i64(1), i64(1), i64(1), i64(1), i64(1), None) == -1
     dummy = ctypes.c_void_p(16)
-    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, sz(1 << 20),
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, None, dummy, sz(1 << 20),
                                i64(1), i64(1), i64(1000), i64(1), i64(1), None) == -2   # D > 768
-    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, sz(16),
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, None, dummy, sz(16),
                                i64(1), i64(1), i64(8), i64(4), i64(4), None) == -3     # workspace too small
+    assert L.ganet_sga_forward(dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, sz(1 << 20),
+                               i64(1), i64(1), i64(300), i64(1), i64(1), None) == -2   # kept aggregates need D <= 288
     dims = (i64(2), i64(3), i64(4), i64(5), i64(6))
     S, HW = 4 * 5 * 6, 5 * 6
     fmin, fbest = L.ganet_sga_forward_workspace_min(*dims), L.ganet_sga_forward_workspace_best(*dims)
     bmin, bbest = L.ganet_sga_backward_workspace_min(*dims), L.ganet_sga_backward_workspace_best(*dims)
-    assert 9 * S + 40 * HW <= fmin <= 9 * S + 40 * HW + 5 * 256      # xT, outT (f32) + maskT (u8) + 2 guidance
+    assert 12 * S + 40 * HW <= fmin <= 12 * S + 40 * HW + 6 * 256    # xT + two aggregates (f32) + 2 guidance
     assert 17 * S + 40 * HW <= bmin <= 17 * S + 40 * HW + 7 * 256    # a, xT, goT, giT + maskT + g, gg
     assert fmin < fbest <= 6 * fmin and bmin < bbest <= 6 * bmin
     d2 = ctypes.c_void_p(32)
