@@ -687,10 +687,11 @@ struct FwdWs { size_t xT, outT, maskT, t3, gT2, gT3, total; };
 static FwdWs fwd_ws(long long n, long long S, long long HW, bool keep = false)
 {
     FwdWs w; size_t o = 0;
-    w.xT = o;    o += align_up((size_t)n * S * 4);
-    w.outT = o;  o += align_up((size_t)n * S * 4);     // keep: `right` aggregate back in the standard layout
+    // keep: xT and the aggregates live in the caller's buffer; only the guidance is staged here
+    w.xT = o;    o += keep ? 0 : align_up((size_t)n * S * 4);
+    w.outT = o;  o += keep ? 0 : align_up((size_t)n * S * 4);
     w.maskT = o; o += keep ? 0 : align_up((size_t)n * S);
-    w.t3 = o;    o += keep ? align_up((size_t)n * S * 4) : 0;   // keep: `left` aggregate, standard layout
+    w.t3 = o;
     w.gT2 = o;   o += align_up((size_t)n * 5 * HW * 4);
     w.gT3 = o;   o += align_up((size_t)n * 5 * HW * 4);
     w.total = o;
@@ -702,7 +703,7 @@ static BwdWs bwd_ws(long long n, long long S, long long HW, bool kept = false)
 {
     BwdWs w; size_t o = 0;
     w.a = o;     o += kept ? 0 : align_up((size_t)n * S * 4);    // kept aggregates: no recompute scratch
-    w.xT = o;    o += align_up((size_t)n * S * 4);
+    w.xT = o;    o += kept ? 0 : align_up((size_t)n * S * 4);    // ... and xT is kept as well
     w.goT = o;   o += align_up((size_t)n * S * 4);
     w.maskT = o; o += align_up((size_t)n * S);
     w.giT = o;   o += align_up((size_t)n * S * 4);
@@ -729,7 +730,7 @@ GANET_API size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D
 {
     (void)N; (void)C;
     const size_t a = fwd_ws(1, D * H * W, H * W, false).total, b = fwd_ws(1, D * H * W, H * W, true).total;
-    return a > b ? a : b;          // one size serves both forward variants
+    return a > b ? a : b;          // one size serves both forward variants (the plain one is larger)
 }
 GANET_API size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
@@ -792,11 +793,11 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
             // buffer (down, up in the standard layout; right, left transposed -- the layouts
             // backward consumes), one streaming kernel merges the four.  Backward then skips
             // its four recompute passes.
-            float *xT = (float *)(ws + w.xT), *t2 = (float *)(ws + w.outT), *t3 = (float *)(ws + w.t3);
             float *gT2 = (float *)(ws + w.gT2), *gT3 = (float *)(ws + w.gT3);
             const float *xs = x + s0 * S;
             float *A0 = aggregates + 0 * ns * S + s0 * S, *A1 = aggregates + 1 * ns * S + s0 * S;
             float *A2T = aggregates + 2 * ns * S + s0 * S, *A3T = aggregates + 3 * ns * S + s0 * S;
+            float *xT = aggregates + 4 * ns * S + s0 * S;      // kept too: backward skips its T(x)
             if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_down + s0 * 5 * HW, A0, nullptr, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
             if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_up + s0 * 5 * HW, A1, nullptr, 1, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
             if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
@@ -804,9 +805,7 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
             if ((rc = launch_transpose<float, false>(g_left + s0 * 5 * HW, gT3, n * 5, iH, iW, st))) return rc;
             if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT2, A2T, nullptr, 0, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
             if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT3, A3T, nullptr, 1, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
-            if ((rc = launch_transpose<float, false>(A2T, t2, n * D, iW, iH, st))) return rc;
-            if ((rc = launch_transpose<float, false>(A3T, t3, n * D, iW, iH, st))) return rc;
-            if ((rc = launch_merge4(A0, A1, t2, t3, out + s0 * S, mask + s0 * S, n * S, st))) return rc;
+            if ((rc = launch_merge4_transposed(A0, A1, A2T, A3T, out + s0 * S, mask + s0 * S, n * D, iH, iW, st))) return rc;
             continue;
         }
         float *xT = (float *)(ws + w.xT), *outT = (float *)(ws + w.outT);
@@ -937,7 +936,8 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
             if ((rc = run_vert_bwd(vc, xs, g[dir] + s0 * 5 * HW, ak, ms, gos, gis, gg[dir] + s0 * 5 * HW, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
         }
         // horizontal directions on the transposed slices
-        if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
+        if (kept) xT = const_cast<float *>(aggregates) + 4 * ns * S + s0 * S;
+        else if ((rc = launch_transpose<float, false>(xs, xT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose<float, false>(gos, goT, n * D, iH, iW, st))) return rc;
         if ((rc = launch_transpose_u8(ms, maskT, n * D, iH, iW, st))) return rc;
         for (int dir = 2; dir < 4; dir++) {

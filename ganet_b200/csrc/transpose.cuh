@@ -161,6 +161,61 @@ static int launch_merge4(const float *a0, const float *a1, const float *a2, cons
     return GANET_OK;
 }
 
+// The same merge with the two horizontal aggregates still TRANSPOSED (planes of W x H): they
+// are read through padded 32x32 shared-memory tiles, so no separate back-transpose pass (and
+// no intermediate volumes) is needed.  a0, a1, out, mask: planes of H x W.
+__global__ void __launch_bounds__(256)
+merge4_transposed_kernel(const float *__restrict__ a0, const float *__restrict__ a1,
+                         const float *__restrict__ a2t, const float *__restrict__ a3t,
+                         float *__restrict__ out, uint8_t *__restrict__ mask, int H, int W)
+{
+    __shared__ float t2[32][33], t3[32][33];
+    const long long plane = blockIdx.z;
+    const long long pb = plane * (long long)H * W;
+    const int w0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {                              // rows of the transposed planes = w
+        const int w = w0 + ty + k, h = h0 + tx;
+        if (w < W && h < H) {
+            t2[ty + k][tx] = __ldg(a2t + pb + (long long)w * H + h);
+            t3[ty + k][tx] = __ldg(a3t + pb + (long long)w * H + h);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int h = h0 + ty + k, w = w0 + tx;
+        if (h < H && w < W) {
+            const long long e = pb + (long long)h * W + w;
+            float b = __ldg(a0 + e);
+            uint8_t id = 0;
+            const float v1 = __ldg(a1 + e), v2 = t2[tx][ty + k], v3 = t3[tx][ty + k];
+            if (b < v1) { b = v1; id = 1; }
+            if (b < v2) { b = v2; id = 2; }
+            if (b < v3) { b = v3; id = 3; }
+            out[e] = b;
+            mask[e] = id;
+        }
+    }
+}
+
+static int launch_merge4_transposed(const float *a0, const float *a1, const float *a2t, const float *a3t,
+                                    float *out, uint8_t *mask, long long planes, int H, int W,
+                                    cudaStream_t st)
+{
+    if (planes <= 0) return GANET_OK;
+    const long long zmax = 65535;
+    for (long long z0 = 0; z0 < planes; z0 += zmax) {
+        const long long nz = planes - z0 < zmax ? planes - z0 : zmax;
+        const long long o = z0 * (long long)H * W;
+        dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32), (unsigned)nz);
+        merge4_transposed_kernel<<<grid, 256, 0, st>>>(a0 + o, a1 + o, a2t + o, a3t + o, out + o, mask + o, H, W);
+    }
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
 // first arg-max over depth per pixel of a TRANSPOSED aggregate aT[D][W][H], written in
 // the standard layout idx[H][W] (MaxDepth, GANet_kernel.cu:50-64)
 __global__ void __launch_bounds__(256)

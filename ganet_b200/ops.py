@@ -36,8 +36,8 @@ def _workspace(x, ws_min, ws_best, workspace_bytes):
 
 
 def keep_aggregates_policy(x, needs_backward=True):
-    """Should forward keep the four directional aggregates (16 bytes per voxel) so that
-    backward can skip its recompute passes?  GANET_B200_KEEP_AGGREGATES = 0 | 1 | auto
+    """Should forward keep the four directional aggregates and the transposed input (20 bytes
+    per voxel) so that backward can skip its recompute passes and one transpose?  GANET_B200_KEEP_AGGREGATES = 0 | 1 | auto
     (default auto: yes when a backward will follow, D <= 288 and three times the buffer is
     still free on the device -- a 180 GB B200 is there to be used)."""
     mode = os.environ.get("GANET_B200_KEEP_AGGREGATES", "auto")
@@ -46,11 +46,11 @@ def keep_aggregates_policy(x, needs_backward=True):
     if mode == "1":
         return True
     free, _ = torch.cuda.mem_get_info(x.device)
-    return free >= 3 * 16 * x.numel()
+    return free >= 3 * 20 * x.numel()
 
 
 def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None, keep_aggregates=False):
-    """-> out (N,C,D,H,W) f32, mask (N,C,D,H,W) u8 [, aggregates (4, N*C*D*H*W) f32]"""
+    """-> out (N,C,D,H,W) f32, mask (N,C,D,H,W) u8 [, aggregates (5, N*C*D*H*W) f32]"""
     N, C, D, H, W = x.shape
     for g in (g0, g1, g2, g3):
         if tuple(g.shape) != (N, C, 5, H, W):
@@ -64,7 +64,7 @@ def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None, keep_aggregates=False):
         dims = _dims5(x)
         ws, ws_bytes = _workspace(x, L.ganet_sga_forward_workspace_min(*dims),
                                   L.ganet_sga_forward_workspace_best(*dims), workspace_bytes)
-        agg = torch.empty((4, x.numel()), dtype=x.dtype, device=x.device) if keep_aggregates else None
+        agg = torch.empty((5, x.numel()), dtype=x.dtype, device=x.device) if keep_aggregates else None
         check(L.ganet_sga_forward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(out),
                                   ptr(mask, torch.uint8), ptr(agg) if agg is not None else None,
                                   ptr(ws, torch.uint8), _lib._sz(ws_bytes), *dims, stream()))
@@ -97,8 +97,8 @@ def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspac
         dims = _dims5(x)
         ws, ws_bytes = _workspace(x, L.ganet_sga_backward_workspace_min(*dims),
                                   L.ganet_sga_backward_workspace_best(*dims), workspace_bytes)
-        if aggregates is not None and tuple(aggregates.shape) != (4, x.numel()):
-            raise ValueError("aggregates must be the (4, x.numel()) tensor returned by sga_forward")
+        if aggregates is not None and tuple(aggregates.shape) != (5, x.numel()):
+            raise ValueError("aggregates must be the (5, x.numel()) tensor returned by sga_forward")
         check(L.ganet_sga_backward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3),
                                    ptr(mask, torch.uint8),
                                    ptr(aggregates) if aggregates is not None else None,

@@ -66,12 +66,12 @@ const char *ganet_error_string(int code);
  *       L1-normalised them over dim 2 (models/GANet_deep.py:265-268)
  *   mask   : (N, C, D, H, W) uint8, winning direction 0=down 1=up 2=right
  *       3=left, ties keep the lower id (GANet_kernel.cu:23-36)
- *   aggregates : optional (may be NULL).  4 * N*C*D*H*W floats that receive the four
+ *   aggregates : optional (may be NULL).  5 * N*C*D*H*W floats that receive the four
  *       directional aggregates -- down, up as (N,C,D,H,W); right, left TRANSPOSED as
- *       (N,C,D,W,H) -- for ganet_sga_backward, which then skips its four recompute
- *       passes (-11 % DRAM traffic for forward+backward, +16 bytes per voxel of saved
- *       state; the reference saves 8: temp_out and an fp32 mask, functions/GANet.py:21).
- *       Needs D <= 288.
+ *       (N,C,D,W,H) -- and the H<->W transposed input, for ganet_sga_backward, which
+ *       then skips its four recompute passes and one transpose (-20 % SGA time for
+ *       forward+backward; +20 bytes per voxel of saved state -- the reference saves 8:
+ *       temp_out and an fp32 mask, functions/GANet.py:21).  Needs D <= 288.
  *   workspace : device scratch (transposed copies for the horizontal scans),
  *       >= ganet_sga_forward_workspace_min bytes; the (n,c) slices are processed
  *       in chunks that fit, so any size between _min and _best works

@@ -152,6 +152,7 @@ def test_kept_aggregates_give_identical_results(ops, shape):
     for d in (2, 3):
         a = ops.sga_direction(xt, gt[d], d)
         assert torch.equal(agg[d].view(*shape[:3], shape[4], shape[3]), a.transpose(3, 4).contiguous())
+    assert torch.equal(agg[4].view(*shape[:3], shape[4], shape[3]), xt.transpose(3, 4).contiguous())
     ref = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True)
     for wsb in (None, 1):
         got2 = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True, aggregates=agg, workspace_bytes=wsb)

@@ -70,7 +70,7 @@ def test_argument_validation_without_gpu(native_so):
     S, HW = 4 * 5 * 6, 5 * 6
     fmin, fbest = L.ganet_sga_forward_workspace_min(*dims), L.ganet_sga_forward_workspace_best(*dims)
     bmin, bbest = L.ganet_sga_backward_workspace_min(*dims), L.ganet_sga_backward_workspace_best(*dims)
-    assert 12 * S + 40 * HW <= fmin <= 12 * S + 40 * HW + 6 * 256    # xT + two aggregates (f32) + 2 guidance
+    assert 9 * S + 40 * HW <= fmin <= 9 * S + 40 * HW + 6 * 256      # xT, outT (f32) + maskT (u8) + 2 guidance
     assert 17 * S + 40 * HW <= bmin <= 17 * S + 40 * HW + 7 * 256    # a, xT, goT, giT + maskT + g, gg
     assert fmin < fbest <= 6 * fmin and bmin < bbest <= 6 * bmin
     d2 = ctypes.c_void_p(32)
