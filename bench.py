@@ -413,10 +413,10 @@ def run_ours(a):
     # chunk, LGA2 fwd 2, LGA2 bwd 4 -- per sample per step
     # launches per native call when the workspace holds the whole call in one chunk:
     # SGA fwd 9 (3 transposes, 2 horizontal scans, 2 back-transposes, 2 vertical scans) or, keeping
-    # the aggregates, 10 (4 raw scans, 5 transposes, 1 merge); SGA bwd 16, or 12 without the four
-    # recompute scans; LGA2 fwd 2, LGA2 bwd 4
+    # the aggregates, 8 (4 raw scans, 3 transposes, 1 merge); SGA bwd 16, or 11 without the four
+    # recompute scans and T(x); LGA2 fwd 2, LGA2 bwd 4
     calls = a.steps * -(-len(mine) // cs)
-    launches = calls * ((10 + 12 if keep_flag[0] else 9 + 16) + 2 + 4)
+    launches = calls * ((8 + 11 if keep_flag[0] else 9 + 16) + 2 + 4)
 
     # ---- roofline of the single hottest kernel family, timed alone ------------------
     # one directional aggregate = ONE launch of the TMA scan kernel in RAW mode: reads x and the

@@ -22,13 +22,21 @@ transpose_planes_kernel(const T *__restrict__ src, T *dst, int R, int Cc)
         const int r = r0 + ty + k, c = c0 + tx;
         if (r < R && c < Cc) tile[ty + k][tx] = sp[(long long)r * Cc + c];
     }
+    T old[4];                                                  // ACC: fetched before the barrier so
+    if (ACC) {                                                 // both load groups are in flight together
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+            const int c = c0 + ty + k, r = r0 + tx;
+            old[k / 8] = (r < R && c < Cc) ? dp[(long long)c * R + r] : T(0);
+        }
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int c = c0 + ty + k, r = r0 + tx;                // dst row = c, dst col = r
         if (r < R && c < Cc) {
             const long long e = (long long)c * R + r;
-            if (ACC) dp[e] = dp[e] + tile[tx][ty + k];
+            if (ACC) dp[e] = old[k / 8] + tile[tx][ty + k];
             else dp[e] = tile[tx][ty + k];
         }
     }
@@ -182,15 +190,23 @@ merge4_transposed_kernel(const float *__restrict__ a0, const float *__restrict__
             t3[ty + k][tx] = __ldg(a3t + pb + (long long)w * H + h);
         }
     }
+    float p0[4], p1[4];                                            // standard-layout operands, fetched
+#pragma unroll                                                     // before the barrier
+    for (int k = 0; k < 32; k += 8) {
+        const int h = h0 + ty + k, w = w0 + tx;
+        const bool ok = h < H && w < W;
+        p0[k / 8] = ok ? __ldg(a0 + pb + (long long)h * W + w) : 0.f;
+        p1[k / 8] = ok ? __ldg(a1 + pb + (long long)h * W + w) : 0.f;
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int h = h0 + ty + k, w = w0 + tx;
         if (h < H && w < W) {
             const long long e = pb + (long long)h * W + w;
-            float b = __ldg(a0 + e);
+            float b = p0[k / 8];
             uint8_t id = 0;
-            const float v1 = __ldg(a1 + e), v2 = t2[tx][ty + k], v3 = t3[tx][ty + k];
+            const float v1 = p1[k / 8], v2 = t2[tx][ty + k], v3 = t3[tx][ty + k];
             if (b < v1) { b = v1; id = 1; }
             if (b < v2) { b = v2; id = 2; }
             if (b < v3) { b = v3; id = 3; }
