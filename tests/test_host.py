@@ -215,3 +215,25 @@ def test_bench_shard_plan_and_roofline_arithmetic():
     # SGA fwd+bwd = 22 + 240/D bytes per voxel, LGA2 = 20 + 900/D
     assert abs(bench.sga_bytes_per_voxel(192) - 23.25) < 1e-9
     assert abs(bench.lga2_bytes_per_voxel(192) - 24.6875) < 1e-9
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver launches next to ours) prints exactly
+    one JSON line with the contract keys; rank != 0 prints nothing and exits 0."""
+    import json
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+           "--warmup", "0", "--batch", "1", "--channels", "2", "--depth", "8", "--height", "8", "--width", "16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+    r2 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
