@@ -15,7 +15,10 @@
 // pixel instead of once per voxel, the x neighbourhood comes from L1 (adjacent
 // threads share it), and every output is accumulated in a register and written
 // once (the reference does 75 global read-modify-writes per voxel).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "lga_tile.cuh"
 
 namespace ganet {
 
@@ -302,11 +305,11 @@ lga_bwd_data_kernel(const float *__restrict__ f, const float *__restrict__ go,
     if (last >= dbeg && last < dend) gxb[(long long)last * HW] = a0;
 }
 
-static int pick_d_chunk(int64_t B, int64_t D, int64_t H, int64_t W)
+static int pick_d_chunk(int64_t B, int64_t D, long long ctas_per_image)
 {
     // enough CTAs to fill 148 SMs a few times over, otherwise keep chunks long so
     // the per-pixel filter load is amortised over many depths
-    const long long ctas = B * H * ((W + kLgaThreads - 1) / kLgaThreads);
+    const long long ctas = B * ctas_per_image;
     long long split = (148ll * 8 + ctas - 1) / ctas;
     if (split < 1) split = 1;
     if (split > D) split = D;
@@ -315,11 +318,62 @@ static int pick_d_chunk(int64_t B, int64_t D, int64_t H, int64_t W)
     return (int)((D + split - 1) / split);
 }
 
+// ---- TMA-tiled variant (lga_tile.cuh): radius 2, rows a multiple of 16 bytes ---------------
+static bool lga_tile_enabled()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("GANET_LGA_NO_TILE") ? 0 : 1;
+    return v != 0;
+}
+
+static bool lga_tile_shape_ok(int64_t B, int64_t D, int64_t H, int64_t W)
+{
+    return lga_tile_enabled() && (W % 4) == 0 && W >= kBW && H >= kBH && D >= kPD &&
+           B * D + kPD < (1ll << 31) && (H + kTH - 1) / kTH <= 65535;
+}
+
+static const int kNoTile = -100;     // internal: use the per-pixel LDG kernels below
+
+// forward (MODE 0: src = x) and data backward (MODE 1: src = gradOut)
+template <int MODE>
+static int lga_tile_launch(const float *src, const float *f, float *dst, int64_t B, int64_t D, int64_t H,
+                           int64_t W, cudaStream_t st)
+{
+    if (!lga_tile_shape_ok(B, D, H, W)) return kNoTile;
+    LgaTileMaps maps;
+    if (!make_plane_map(&maps.src, src, 4, B * D, (int)H, (int)W, kBW, kPD, kBH)) return kNoTile;
+    maps.go = maps.src;
+    const long long tiles = ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH);
+    const int dck = pick_d_chunk(B, D, tiles);
+    const int nchunk = (int)((D + dck - 1) / dck);
+    dim3 grid((unsigned)((W + kTW - 1) / kTW), (unsigned)((H + kTH - 1) / kTH), (unsigned)(B * nchunk));
+    lga_tile_kernel<MODE><<<grid, kTileThreads, 0, st>>>(maps, f, dst, (int)D, (int)H, (int)W, dck);
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int lga_tile_filter_launch(const float *x, const float *go, float *gf, int accumulate, int64_t B,
+                                  int64_t D, int64_t H, int64_t W, cudaStream_t st)
+{
+    if (!lga_tile_shape_ok(B, D, H, W) || B > 65535) return kNoTile;
+    LgaTileMaps maps;
+    if (!make_plane_map(&maps.src, x, 4, B * D, (int)H, (int)W, kBW, kPD, kBH)) return kNoTile;
+    if (!make_plane_map(&maps.go, go, 4, B * D, (int)H, (int)W, kTW, kPD, kTH)) return kNoTile;
+    dim3 grid((unsigned)((W + kTW - 1) / kTW), (unsigned)((H + kTH - 1) / kTH), (unsigned)B);
+    lga_tile_filter_kernel<<<grid, kTileThreads, 0, st>>>(maps, go, gf, accumulate, (int)D, (int)H, (int)W);
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
 template <int R>
 static int lga_forward_r(const float *x, const float *f, float *y, int64_t B, int64_t D,
                          int64_t H, int64_t W, cudaStream_t st)
 {
-    const int dck = pick_d_chunk(B, D, H, W);
+    if (R == kTR) {
+        const int rc = lga_tile_launch<0>(x, f, y, B, D, H, W, st);
+        if (rc != kNoTile) return rc;
+    }
+    const int dck = pick_d_chunk(B, D, H * ((W + kLgaThreads - 1) / kLgaThreads));
     const int nchunk = (int)((D + dck - 1) / dck);
     dim3 grid((unsigned)((W + kLgaThreads - 1) / kLgaThreads), (unsigned)H, (unsigned)(B * nchunk));
     lga_fwd_kernel<R><<<grid, kLgaThreads, 0, st>>>(x, f, y, (int)D, (int)H, (int)W, dck);
@@ -332,11 +386,18 @@ static int lga_backward_r(const float *x, const float *f, const float *go, float
                           int accumulate, int64_t B, int64_t D, int64_t H, int64_t W,
                           cudaStream_t st)
 {
-    dim3 gridf((unsigned)((W + kLgaThreads - 1) / kLgaThreads), (unsigned)H, (unsigned)B);
-    lga_bwd_filter_kernel<R><<<gridf, kLgaThreads, 0, st>>>(x, go, gf, accumulate, (int)D, (int)H,
-                                                            (int)W);
-    GANET_RETURN_IF_LAUNCH_FAILED();
-    const int dck = pick_d_chunk(B, D, H, W);
+    int rc = (R == kTR) ? lga_tile_filter_launch(x, go, gf, accumulate, B, D, H, W, st) : kNoTile;
+    if (rc == kNoTile) {
+        dim3 gridf((unsigned)((W + kLgaThreads - 1) / kLgaThreads), (unsigned)H, (unsigned)B);
+        lga_bwd_filter_kernel<R><<<gridf, kLgaThreads, 0, st>>>(x, go, gf, accumulate, (int)D, (int)H,
+                                                                (int)W);
+        GANET_RETURN_IF_LAUNCH_FAILED();
+    } else if (rc) {
+        return rc;
+    }
+    rc = (R == kTR) ? lga_tile_launch<1>(go, f, gx, B, D, H, W, st) : kNoTile;
+    if (rc != kNoTile) return rc;
+    const int dck = pick_d_chunk(B, D, H * ((W + kLgaThreads - 1) / kLgaThreads));
     const int nchunk = (int)((D + dck - 1) / dck);
     dim3 grid((unsigned)((W + kLgaThreads - 1) / kLgaThreads), (unsigned)H, (unsigned)(B * nchunk));
     lga_bwd_data_kernel<R><<<grid, kLgaThreads, 0, st>>>(f, go, gx, (int)D, (int)H, (int)W, dck);

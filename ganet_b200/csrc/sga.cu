@@ -492,6 +492,15 @@ static bool tma_enabled()
     return v != 0;
 }
 
+// tuning aid: cap the depth of the TMA stage ring (fewer stages = less shared memory per CTA =
+// more resident CTAs per SM)
+static int stage_cap(int dflt)
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GANET_TMA_STAGES"); v = e ? atoi(e) : 0; }
+    return (v >= 2 && v < dflt) ? v : dflt;
+}
+
 // L2 evict-first hints on the TMA traffic.  Measured on B200 at 1x32x192x240x624: WORSE
 // (forward 12.6 -> 15.1 ms, backward 28.1 -> 29.2 ms) -- neighbouring strips and consecutive
 // passes do profit from L2 -- so the hint is off unless GANET_L2_HINT=1 asks for it.
@@ -514,7 +523,7 @@ static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, ui
     const FwdPlan pl = fwd_plan(D, kCombine, kThree);
     const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
     int S = (kSmemBudget - ex_bytes - 128) / pl.stage_bytes;
-    if (S > 6) S = 6;
+    if (S > stage_cap(6)) S = stage_cap(6);
     if (S > H) S = H;
     if (S < 2 && H >= 2) return kNotApplicable;
     const size_t smem = (size_t)S * pl.stage_bytes + ex_bytes + 2 * S * sizeof(uint64_t);

@@ -223,6 +223,36 @@ def test_tma_and_ldg_kernels_agree_bitwise(ops):
     assert digests[0] == digests[1] == digests[2]
 
 
+def test_lga_tiled_and_per_pixel_kernels_agree_bitwise(ops):
+    """The TMA-tiled LGA kernels (lga_tile.cuh) keep the summation order of the per-pixel
+    kernels (lga.cu): same bits.  GANET_LGA_NO_TILE is read once per process -> subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+        "from ganet_b200 import ops; from util import lga_inputs;"
+        "h = hashlib.sha256();"
+        "cu = lambda a: torch.from_numpy(a).cuda();\n"
+        "for shape in [(1, 9, 12, 40), (2, 6, 9, 44), (1, 33, 20, 152)]:\n"
+        "    x, f, go = lga_inputs(shape, seed=13)\n"
+        "    xt, ft, got = cu(x), cu(f), cu(go)\n"
+        "    y = ops.lga_forward(xt, ft, 2)\n"
+        "    gx, gf = ops.lga_backward(xt, ft, got, 2)\n"
+        "    gx2, gf = ops.lga_backward(y, ft, got, 2, gf)\n"
+        "    [h.update(t.cpu().numpy().tobytes()) for t in (y, gx, gx2, gf)]\n"
+        "print(h.hexdigest())"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for knobs in ({}, {"GANET_LGA_NO_TILE": "1"}):
+        env = dict(os.environ)
+        env.pop("GANET_LGA_NO_TILE", None)
+        env.update(knobs)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
+
+
 def test_sga_ties_and_constant_input(ops):
     x = torch.full((1, 2, 6, 5, 7), 0.75, device="cuda")
     g = [torch.full((1, 2, 5, 5, 7), 0.2, device="cuda") for _ in range(4)]
@@ -234,7 +264,11 @@ def test_sga_ties_and_constant_input(ops):
 
 # ---- LGA ---------------------------------------------------------------------
 LGA_SHAPES = [(2, 7, 5, 6), (1, 3, 9, 11), (1, 1, 1, 1), (1, 5, 1, 40), (1, 4, 37, 3),
-              (1, 33, 20, 150), (2, 2, 3, 5, 4)]
+              (1, 33, 20, 150), (2, 2, 3, 5, 4),
+              # W a multiple of 4, W >= 40, H >= 8, D >= 4: the TMA-tiled radius-2 kernels run;
+              # partial tiles in both directions, depth not a multiple of the 4-plane stage,
+              # more stages than the ring holds, the 5-D (lga3d) form
+              (1, 9, 12, 40), (2, 6, 9, 44), (1, 33, 20, 152), (1, 4, 8, 72), (2, 2, 5, 8, 40)]
 
 
 @needs_ref
