@@ -23,6 +23,8 @@ def main():
     src, dst = sys.argv[1], sys.argv[2]
     per_rep = int(sys.argv[3]) if len(sys.argv) > 3 else 31
     voxels = int(sys.argv[4]) if len(sys.argv) > 4 else 32 * 192 * 240 * 624
+    what = sys.argv[5] if len(sys.argv) > 5 else "`python scripts/one_pass.py`: the %d launches of its last repetition, one 920M-voxel sample" % per_rep
+    write_traffic = len(sys.argv) <= 5
     lines = [l for l in open(src) if not l.startswith("==")]
     per = collections.OrderedDict()
     for r in csv.DictReader(lines):
@@ -31,7 +33,7 @@ def main():
             (T.get(r["Metric Unit"], None) if r["Metric Name"].startswith("gpu__time") else F[r["Metric Unit"]])
     items = list(per.items())
     last = items[-per_rep:]                 # the last repetition (warm)
-    out = ["# ncu launch list of `python scripts/one_pass.py`: the %d launches of its last repetition, one 920M-voxel sample" % per_rep,
+    out = ["# ncu launch list of " + what,
            "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes",
            "%-4s %-58s %9s %9s %9s %8s" % ("id", "kernel", "ms", "rd GB", "wr GB", "GB/s")]
     tot = collections.Counter()
@@ -54,6 +56,9 @@ def main():
     out.append("total %.2f ms; SGA launches %.2f ms, %.1f GB DRAM = %.1f B/voxel (algorithmic 23.25)"
                % (tot["ms"], sga["ms"], sga["bytes"] / 1e9, sga["bytes"] / voxels))
     open(dst, "w").write("\n".join(out) + "\n")
+    if not write_traffic:
+        print("\n".join(out[-8:]))
+        return
     tj = {"op": "SGA forward+backward, all launches of one call", "dram_bytes_per_voxel": sga["bytes"] / voxels,
           "dram_bytes_per_call": sga["bytes"], "voxels_per_call": voxels, "source": os.path.basename(dst)}
     json.dump(tj, open(os.path.join(os.path.dirname(dst) or ".", "traffic.json"), "w"), indent=1)
