@@ -359,7 +359,8 @@ sga_tma_hraw_kernel(const __grid_constant__ TmaHrawMaps maps, int D, int W, int 
 
 // ---------------------------------------------------------------------------
 // backward (reverse sweep).  gradInput leaves through the gradOut tile (in place);
-// when accumulating, the old gradInput row is read with plain coalesced loads.
+// accumulate = 1: the old gradInput row is read with plain coalesced loads and added here;
+// accumulate = 2: the tile leaves as a TMA reduce-add, nothing is read back.
 // The guidance gradients (5 floats per pixel) are written directly by warps 0..4.
 // ---------------------------------------------------------------------------
 template <int K, int MAXW, bool FULL>
@@ -419,7 +420,8 @@ sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old,
                 const int st = it % S;
                 mbar_wait(&done[st], (it / S) & 1);
                 unsigned char *b = smem + (size_t)st * pl.stage_bytes;
-                tma_store_3d(&maps.gi, b + pl.off_go, w0, row_of(H - 1 - it), c2x);
+                if (accumulate == 2) tma_reduce_add_3d(&maps.gi, b + pl.off_go, w0, row_of(H - 1 - it), c2x);
+                else tma_store_3d(&maps.gi, b + pl.off_go, w0, row_of(H - 1 - it), c2x);
                 tma_commit();
                 if (it + S < H) {
                     tma_wait_read_all();
@@ -464,7 +466,7 @@ sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old,
         const int st = it % S;
         unsigned char *b = smem + (size_t)st * pl.stage_bytes;
         float gold[K];
-        if (accumulate) {                                   // issued before the wait: overlaps it
+        if (accumulate == 1) {                              // issued before the wait: overlaps it
 #pragma unroll
             for (int i = 0; i < K; i++)
                 gold[i] = (FULL || d0 + i < D) ? *at<const float>(girow, offb[i]) : 0.f;

@@ -79,6 +79,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
         : "memory");
 }
 
+// gradInput accumulation without reading it into the SM: the memory system adds the tile to
+// what is stored (one writer per element and pass, round-to-nearest: the same bits as a
+// load + fadd + store, except that fp32 subnormals are flushed)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const void *src, int c0, int c1,
+                                                  int c2)
+{
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // streaming variants: L2 evict-first policy (the volumes are far larger than L2 and every
 // tile is touched once per pass)
 __device__ __forceinline__ uint64_t l2_evict_first_policy()
