@@ -216,17 +216,82 @@ merge4_transposed_kernel(const float *__restrict__ a0, const float *__restrict__
     }
 }
 
+// Wide variant for W % 4 == 0: a CTA covers 128 columns x 32 rows, so the 1-byte mask leaves as
+// 128-byte rows of 32-bit words (the 32-byte rows of the kernel above are what held it at
+// 4.6 TB/s; cf. the byte-plane transpose) and 64 loads per thread are in flight before the barrier.
+__global__ void __launch_bounds__(256)
+merge4_transposed_wide_kernel(const float *__restrict__ a0, const float *__restrict__ a1,
+                              const float *__restrict__ a2t, const float *__restrict__ a3t,
+                              float *__restrict__ out, uint8_t *__restrict__ mask, int H, int W)
+{
+    __shared__ float t2[4][32][33], t3[4][32][33];
+    __shared__ __align__(16) uint8_t mk[32][128];
+    const long long plane = blockIdx.z;
+    const long long pb = plane * (long long)H * W;
+    const int w0 = blockIdx.x * 128, h0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {                          // rows of the transposed planes = w
+            const int w = w0 + 32 * q + ty + k, h = h0 + tx;
+            if (w < W && h < H) {
+                t2[q][ty + k][tx] = __ldg(a2t + pb + (long long)w * H + h);
+                t3[q][ty + k][tx] = __ldg(a3t + pb + (long long)w * H + h);
+            }
+        }
+    float p0[16], p1[16];                                          // standard-layout operands
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+            const int h = h0 + ty + k, w = w0 + 32 * q + tx;
+            const bool ok = h < H && w < W;
+            p0[q * 4 + k / 8] = ok ? __ldg(a0 + pb + (long long)h * W + w) : 0.f;
+            p1[q * 4 + k / 8] = ok ? __ldg(a1 + pb + (long long)h * W + w) : 0.f;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+            const int h = h0 + ty + k, w = w0 + 32 * q + tx;
+            float b = p0[q * 4 + k / 8];
+            uint8_t id = 0;
+            const float v1 = p1[q * 4 + k / 8], v2 = t2[q][tx][ty + k], v3 = t3[q][tx][ty + k];
+            if (b < v1) { b = v1; id = 1; }
+            if (b < v2) { b = v2; id = 2; }
+            if (b < v3) { b = v3; id = 3; }
+            if (h < H && w < W) out[pb + (long long)h * W + w] = b;
+            mk[ty + k][32 * q + tx] = id;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {                              // one 32-bit word per lane: 128-byte rows
+        const int h = h0 + ty + k, w = w0 + 4 * tx;
+        if (h < H && w < W)                                        // W % 4 == 0: a word is inside or outside
+            *reinterpret_cast<uint32_t *>(mask + pb + (long long)h * W + w) =
+                *reinterpret_cast<const uint32_t *>(&mk[ty + k][4 * tx]);
+    }
+}
+
 static int launch_merge4_transposed(const float *a0, const float *a1, const float *a2t, const float *a3t,
                                     float *out, uint8_t *mask, long long planes, int H, int W,
                                     cudaStream_t st)
 {
     if (planes <= 0) return GANET_OK;
+    const bool wide = (W % 4) == 0 && (((uintptr_t)mask) & 3) == 0 && ((long long)H * W) % 4 == 0;
     const long long zmax = 65535;
     for (long long z0 = 0; z0 < planes; z0 += zmax) {
         const long long nz = planes - z0 < zmax ? planes - z0 : zmax;
         const long long o = z0 * (long long)H * W;
-        dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32), (unsigned)nz);
-        merge4_transposed_kernel<<<grid, 256, 0, st>>>(a0 + o, a1 + o, a2t + o, a3t + o, out + o, mask + o, H, W);
+        if (wide) {
+            dim3 grid((unsigned)((W + 127) / 128), (unsigned)((H + 31) / 32), (unsigned)nz);
+            merge4_transposed_wide_kernel<<<grid, 256, 0, st>>>(a0 + o, a1 + o, a2t + o, a3t + o, out + o, mask + o, H, W);
+        } else {
+            dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 31) / 32), (unsigned)nz);
+            merge4_transposed_kernel<<<grid, 256, 0, st>>>(a0 + o, a1 + o, a2t + o, a3t + o, out + o, mask + o, H, W);
+        }
     }
     GANET_RETURN_IF_LAUNCH_FAILED();
     return GANET_OK;
