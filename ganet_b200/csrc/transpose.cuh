@@ -110,66 +110,7 @@ static int launch_transpose_u8(const uint8_t *src, uint8_t *dst, long long plane
 
 // out = max of the four directional aggregates, mask = the first direction attaining it
 // (strict < in the order down, up, right, left: the reference's Max chain, GANet_kernel.cu
-// :23-36, :975-994).  Pure streaming: 16 bytes in, 5 bytes out per voxel, 128-bit accesses.
-__global__ void __launch_bounds__(256)
-merge4_kernel(const float4 *__restrict__ a0, const float4 *__restrict__ a1,
-              const float4 *__restrict__ a2, const float4 *__restrict__ a3,
-              float4 *__restrict__ out, uchar4 *__restrict__ mask, long long n4)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 v0 = __ldg(a0 + i), v1 = __ldg(a1 + i), v2 = __ldg(a2 + i), v3 = __ldg(a3 + i);
-    float4 o;
-    uchar4 m;
-#define GANET_MERGE(c)                                              \
-    {                                                               \
-        float b = v0.c; unsigned char id = 0;                       \
-        if (b < v1.c) { b = v1.c; id = 1; }                         \
-        if (b < v2.c) { b = v2.c; id = 2; }                         \
-        if (b < v3.c) { b = v3.c; id = 3; }                         \
-        o.c = b; m.c = id;                                          \
-    }
-    GANET_MERGE(x) GANET_MERGE(y) GANET_MERGE(z) GANET_MERGE(w)
-#undef GANET_MERGE
-    out[i] = o;
-    mask[i] = m;
-}
-
-// scalar tail / unaligned fallback
-__global__ void __launch_bounds__(256)
-merge4_scalar_kernel(const float *__restrict__ a0, const float *__restrict__ a1,
-                     const float *__restrict__ a2, const float *__restrict__ a3,
-                     float *__restrict__ out, uint8_t *__restrict__ mask, long long n)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float b = a0[i]; uint8_t id = 0;
-    if (b < a1[i]) { b = a1[i]; id = 1; }
-    if (b < a2[i]) { b = a2[i]; id = 2; }
-    if (b < a3[i]) { b = a3[i]; id = 3; }
-    out[i] = b;
-    mask[i] = id;
-}
-
-static int launch_merge4(const float *a0, const float *a1, const float *a2, const float *a3, float *out,
-                         uint8_t *mask, long long n, cudaStream_t st)
-{
-    if (n <= 0) return GANET_OK;
-    const bool vec = (n % 4 == 0) && !(((uintptr_t)a0 | (uintptr_t)a1 | (uintptr_t)a2 | (uintptr_t)a3 |
-                                        (uintptr_t)out) & 15) && !((uintptr_t)mask & 3);
-    if (vec) {
-        const long long n4 = n / 4;
-        merge4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
-            (const float4 *)a0, (const float4 *)a1, (const float4 *)a2, (const float4 *)a3, (float4 *)out,
-            (uchar4 *)mask, n4);
-    } else {
-        merge4_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a0, a1, a2, a3, out, mask, n);
-    }
-    GANET_RETURN_IF_LAUNCH_FAILED();
-    return GANET_OK;
-}
-
-// The same merge with the two horizontal aggregates still TRANSPOSED (planes of W x H): they
+// :23-36, :975-994), with the two horizontal aggregates still TRANSPOSED (planes of W x H): they
 // are read through padded 32x32 shared-memory tiles, so no separate back-transpose pass (and
 // no intermediate volumes) is needed.  a0, a1, out, mask: planes of H x W.
 __global__ void __launch_bounds__(256)
