@@ -6,8 +6,8 @@
 A "step" is one pass of the hot path -- SGA forward+backward and LGA2
 forward+backward -- over one synthetic batch B x C x D x H x W = 8 x 32 x 192 x
 240 x 624 (BASELINE.json; SURVEY.md 8d for the input recipe).  The batch axis is
-sharded over the ranks (no data-path collective: SURVEY.md 8e); on one GPU the
-batch is walked one sample at a time.  Rank 0 prints ONE JSON line.
+sharded over the ranks (no data-path collective: SURVEY.md 8e); a rank walks its
+shard --chunk samples (default 2) per native call.  Rank 0 prints ONE JSON line.
 
   value      voxels/s = (B*C*D*H*W + B*D*H*W) * K / max-over-ranks device time,
              inputs resident in HBM, timed with CUDA events on the launch stream
