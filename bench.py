@@ -340,6 +340,11 @@ def run_ours(a):
     phase_events = []
 
     cs = max(1, min(a.chunk, max(1, len(mine))))
+    # The kept-aggregates variant needs 20 bytes per voxel of the call; if the policy (the rule
+    # SgaFunction applies under autograd: three times the buffer still free) says no for this
+    # many samples per call, smaller calls are better than falling back to the recompute variant.
+    while cs > 1 and mine and not ops.keep_aggregates_policy(x[0:cs], True):
+        cs //= 2
     keep_flag = [None]
 
     def one_sample(i, record):
