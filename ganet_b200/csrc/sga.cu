@@ -411,8 +411,10 @@ static bool pick_vert_cfg(int D, VCfg *out)
 {
     static const int ks[] = {2, 4, 6, 12, 24};
     static const int mw[] = {16, 16, 16, 16, 12};
-    if (const char *env = getenv("GANET_VERT_K")) {            // tuning aid
-        const int k = atoi(env);
+    static int forced_k = -1;                                   // tuning aid, read once
+    if (forced_k < 0) { const char *env = getenv("GANET_VERT_K"); forced_k = env ? atoi(env) : 0; }
+    if (forced_k > 0) {
+        const int k = forced_k;
         for (int i = 0; i < 5; i++)
             if (ks[i] == k && (D + k - 1) / k <= (k == 6 ? 32 : mw[i])) { out->K = k; out->NW = (D + k - 1) / k; return true; }
     }
@@ -661,8 +663,11 @@ static int launch_tma_hraw(VCfg c, const float *x, const float *g, float *out, i
 // slower beyond (1x32x192x240x624: 33.8 vs 12.8 ms) -- so it is used for small calls only.
 static bool fwd_direct_ok(VCfg c, int D, int H, int W, long long voxels)
 {
-    if (!tma_enabled() || getenv("GANET_NO_DIRECT") || D > 256 || (W % 16) != 0 || H < 32) return false;
-    if (voxels > 48ll * 1000 * 1000 && !getenv("GANET_FORCE_DIRECT")) return false;
+    static int no_direct = -1, force_direct = -1;               // read once
+    if (no_direct < 0) no_direct = getenv("GANET_NO_DIRECT") ? 1 : 0;
+    if (force_direct < 0) force_direct = getenv("GANET_FORCE_DIRECT") ? 1 : 0;
+    if (!tma_enabled() || no_direct || D > 256 || (W % 16) != 0 || H < 32) return false;
+    if (voxels > 48ll * 1000 * 1000 && !force_direct) return false;
     const int ex_bytes = 2 * 3 * c.NW * 32 * 4;
     if ((kSmemBudget - ex_bytes - 128) / (D * 512 + 2560) < 2) return false;
     if ((kSmemBudget - ex_bytes - 128) / fwd_plan(D, true, true).stage_bytes < 2) return false;
@@ -967,8 +972,12 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
             if (!kept)
                 if ((rc = run_vert_fwd<VMODE_RAW>(vc, xT, gT, a, nullptr, dir - 2, MaskIds{0, 0}, iD, iW, iH, n, st))) return rc;
             if (max_idx && dir == 2) {
-                dim3 grid((unsigned)((HW + 255) / 256), (unsigned)n);
-                max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(ak, max_idx + s0 * HW, iD, iH, iW);
+                for (long long z0 = 0; z0 < n; z0 += 65535) {          // gridDim.y limit
+                    const long long nz = n - z0 < 65535 ? n - z0 : 65535;
+                    dim3 grid((unsigned)((HW + 255) / 256), (unsigned)nz);
+                    max_depth_from_transposed_kernel<<<grid, 256, 0, st>>>(ak + z0 * S, max_idx + (s0 + z0) * HW,
+                                                                           iD, iH, iW);
+                }
                 GANET_RETURN_IF_LAUNCH_FAILED();
             }
             if ((rc = run_vert_bwd(vc, xT, gT, ak, maskT, goT, giT, ggT, dir - 2, dir, dir > 2, iD, iW, iH, n, st))) return rc;
