@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import api, ref_cpu
-from util import lga_inputs, sga_inputs
+from util import assert_close, lga_inputs, sga_inputs
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -183,3 +183,46 @@ def test_disparity_regression():
     g = rng.standard_normal((2, 3, 5)).astype(np.float32)
     gp = api.disp_regression_backward(g, 7)
     assert np.array_equal(gp, g[:, None] * np.arange(7, dtype=np.float32).reshape(1, 7, 1, 1))
+
+
+# ---- size-independent properties of the path (the ones test_gpu_fullsize.py relies on) ------
+@pytest.mark.parametrize("fused", [False, True])
+def test_power_of_two_scaling_is_exact(fused):
+    """Every operation of the recurrence is a multiply, add, fma or max: scaling x (and the
+    incoming gradient) by 2^k scales every result by 2^k bit for bit and leaves the direction
+    mask and the depth arg-max untouched."""
+    x, g, go = sga_inputs((1, 2, 9, 6, 7), seed=21)
+    out, mask = api.sga_forward(x, *g, fused=fused)
+    gi, gg, idx = api.sga_backward(x, *g, mask, go, fused=fused)
+    out8, mask8 = api.sga_forward(8.0 * x, *g, fused=fused)
+    assert np.array_equal(out8, 8.0 * out) and np.array_equal(mask8, mask)
+    gi4, gg4, idx4 = api.sga_backward(8.0 * x, *g, mask, 0.5 * go, fused=fused)
+    assert np.array_equal(gi4, 0.5 * gi) and np.array_equal(idx4, idx)
+    # guidance gradients are bilinear in (gradOut, x / A): 0.5 * 8 = 4
+    assert all(np.array_equal(a, 4.0 * b) for a, b in zip(gg4, gg))
+
+
+def test_depth_flip_symmetry():
+    """Flipping the depth axis and exchanging the d-1 / d+1 weights (w2 <-> w3) flips the result."""
+    x, g, _ = sga_inputs((1, 2, 8, 5, 6), seed=22)
+    out, mask = api.sga_forward(x, *g, fused=False)
+    gs = [np.ascontiguousarray(a[:, :, [0, 1, 3, 2, 4]]) for a in g]
+    outf, maskf = api.sga_forward(np.ascontiguousarray(x[:, :, ::-1]), *gs, fused=False)
+    assert_close(outf[:, :, ::-1], out, 1e-5, "depth-flipped forward")
+    assert (maskf[:, :, ::-1] != mask).mean() < 0.01        # only fp32 near-ties may flip
+
+
+def test_slices_are_independent():
+    """Nothing couples different (n, c): a batch equals its slices computed alone (what lets the
+    path shard over the batch with no collective, and the native side chunk its workspace)."""
+    x, g, go = sga_inputs((2, 3, 5, 4, 6), seed=23)
+    out, mask = api.sga_forward(x, *g)
+    gi, gg, idx = api.sga_backward(x, *g, mask, go)
+    for n in range(2):
+        for c in range(3):
+            sl = (slice(n, n + 1), slice(c, c + 1))
+            o1, m1 = api.sga_forward(x[sl], *[a[sl] for a in g])
+            assert np.array_equal(o1, out[sl]) and np.array_equal(m1, mask[sl])
+            gi1, gg1, idx1 = api.sga_backward(x[sl], *[a[sl] for a in g], m1, go[sl])
+            assert np.array_equal(gi1, gi[sl]) and np.array_equal(idx1, idx[sl])
+            assert all(np.array_equal(a, b[sl]) for a, b in zip(gg1, gg))
