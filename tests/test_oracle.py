@@ -226,3 +226,45 @@ def test_slices_are_independent():
             gi1, gg1, idx1 = api.sga_backward(x[sl], *[a[sl] for a in g], m1, go[sl])
             assert np.array_equal(gi1, gi[sl]) and np.array_equal(idx1, idx[sl])
             assert all(np.array_equal(a, b[sl]) for a, b in zip(gg1, gg))
+
+
+# ---- randomised shapes against the reference's own kernel bodies ----------------------------
+try:
+    from hypothesis import given, settings, strategies as st
+    _HAVE_HYPOTHESIS = True
+except Exception:                                            # pragma: no cover
+    _HAVE_HYPOTHESIS = False
+
+if _HAVE_HYPOTHESIS:
+    _dims = st.tuples(st.integers(1, 2), st.integers(1, 3), st.integers(1, 13), st.integers(1, 9),
+                      st.integers(1, 9))
+
+    @pytest.mark.skipif(not ref_cpu.available(), reason="oracle/_ref/libganet_ref_cpu.so not built")
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(shape=_dims, seed=st.integers(0, 10 ** 6))
+    def test_oracle_equals_reference_kernel_bodies_on_random_shapes(shape, seed):
+        """Ragged and degenerate volumes (any of D, H, W down to 1): forward, mask, all gradients and
+        the depth arg-max bit for bit against the reference's kernel bodies compiled for the host."""
+        x, g, go = sga_inputs(shape, seed=seed)
+        ro, rm, rt = ref_cpu.sga_forward(x, *g)
+        oo, om, od = api.sga_forward(x, *g, fused=False, want_dirs=True)
+        assert np.array_equal(ro, oo) and np.array_equal(rm.astype(np.uint8), om)
+        assert np.array_equal(rt, od[3])
+        rgi, rgg, ridx = ref_cpu.sga_backward(x, *g, rt, rm, go)
+        ogi, ogg, oidx = api.sga_backward(x, *g, om, go, fused=False)
+        assert np.array_equal(rgi, ogi)
+        assert all(np.array_equal(a, b) for a, b in zip(rgg, ogg))
+        assert np.array_equal(ridx.astype(np.int32), oidx)
+
+    @pytest.mark.skipif(not ref_cpu.available(), reason="oracle/_ref/libganet_ref_cpu.so not built")
+    @settings(max_examples=20, deadline=None, derandomize=True)
+    @given(shape=st.tuples(st.integers(1, 2), st.integers(1, 7), st.integers(1, 8), st.integers(1, 8)),
+           seed=st.integers(0, 10 ** 6))
+    def test_oracle_lga_equals_reference_kernel_bodies_on_random_shapes(shape, seed):
+        x, f, go = lga_inputs(shape, seed=seed)
+        ry, ry1 = ref_cpu.lga2_forward(x, f)
+        oy, otmp = api.lga_forward(x, f, 2, 2)
+        assert np.array_equal(ry, oy) and np.array_equal(ry1, otmp[0])
+        rgx, rgf = ref_cpu.lga2_backward(x, f, ry1, go)
+        ogx, ogf = api.lga_backward(x, f, otmp, go, 2, 2)
+        assert np.array_equal(rgx, ogx) and np.array_equal(rgf, ogf)
