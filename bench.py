@@ -45,6 +45,15 @@ def shard_samples(batch, world, rank):
     return list(range(lo, hi))
 
 
+def samples_per_call(requested, n_mine, fits):
+    """Samples handed to one native call: as requested, halved until `fits(count)` says the
+    kept-aggregates variant has room (smaller calls beat falling back to the recompute variant)."""
+    cs = max(1, min(int(requested), max(1, int(n_mine))))
+    while cs > 1 and not fits(cs):
+        cs //= 2
+    return cs
+
+
 def sga_bytes_per_voxel(D):
     """SGA fwd (9 + 80/D) + bwd (13 + 160/D) algorithmic bytes per voxel."""
     return 22.0 + 240.0 / D
@@ -339,12 +348,9 @@ def run_ours(a):
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     phase_events = []
 
-    cs = max(1, min(a.chunk, max(1, len(mine))))
-    # The kept-aggregates variant needs 20 bytes per voxel of the call; if the policy (the rule
-    # SgaFunction applies under autograd: three times the buffer still free) says no for this
-    # many samples per call, smaller calls are better than falling back to the recompute variant.
-    while cs > 1 and mine and not ops.keep_aggregates_policy(x[0:cs], True):
-        cs //= 2
+    # The kept-aggregates variant needs 20 bytes per voxel of the call; the policy is the rule
+    # SgaFunction applies under autograd (three times the buffer still free on the device).
+    cs = samples_per_call(a.chunk, len(mine), lambda c: ops.keep_aggregates_policy(x[0:c], True))
     keep_flag = [None]
 
     def one_sample(i, record):

@@ -217,6 +217,16 @@ def test_bench_shard_plan_and_roofline_arithmetic():
     assert abs(bench.lga2_bytes_per_voxel(192) - 24.6875) < 1e-9
 
 
+def test_bench_samples_per_call():
+    import bench
+    assert bench.samples_per_call(2, 8, lambda c: True) == 2
+    assert bench.samples_per_call(2, 1, lambda c: True) == 1          # 8 ranks: one sample each
+    assert bench.samples_per_call(4, 8, lambda c: c <= 1) == 1        # no room: shrink, never loop forever
+    assert bench.samples_per_call(4, 8, lambda c: c <= 2) == 2
+    assert bench.samples_per_call(2, 0, lambda c: False) == 1         # a rank without samples
+    assert bench.samples_per_call(3, 8, lambda c: False) == 1
+
+
 def test_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver launches next to ours) prints exactly
     one JSON line with the contract keys; rank != 0 prints nothing and exits 0."""
