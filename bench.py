@@ -264,6 +264,31 @@ def cpu_reference_rates(depth, height, width, seconds):
     }
 
 
+def cpu_config1():
+    """BASELINE.json config 1 -- a single SGA forward on 1x8x48x48x96, the reference's own
+    CPU-runnable case -- timed on the host cores with whatever thread count is set."""
+    import numpy as np
+    from oracle import api as port
+    from oracle import ref_cpu
+    rng = np.random.default_rng(1)
+    shape = (1, 8, 48, 48, 96)
+    x = rng.standard_normal(shape).astype(np.float32)
+    g = []
+    for _ in range(4):
+        a = rng.standard_normal((1, 8, 5, 48, 96))
+        g.append((a / np.abs(a).sum(axis=2, keepdims=True)).astype(np.float32))
+    fwd = ref_cpu.sga_forward if ref_cpu.available() else (lambda *t: port.sga_forward(*t, fused=False))
+    fwd(x, *g)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        fwd(x, *g)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return {"workload": "SGA forward on 1x8x48x48x96 (BASELINE.json config 1)", "ms": 1e3 * best,
+            "voxels_per_s": float(np.prod(shape) / best)}
+
+
 def combine_rates(v_sga, v_lga, r_sga, r_lga):
     return (v_sga + v_lga) / (v_sga / r_sga + v_lga / r_lga)
 
@@ -297,6 +322,7 @@ def run_reference_arm(a):
                          "sample": info["sample"]},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
+        "config1_cpu": cpu_config1(),
         "gpu_launches": 0, "wall_s": wall,
     }
     print(json.dumps(line))
