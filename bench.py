@@ -76,6 +76,45 @@ def dist_setup(backend, device=None):
     return world, rank, local_rank
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (PCI bus id ->
+    /sys/bus/pci/devices/*/numa_node -> node cpulist), BEFORE any pinned host buffer is allocated, so
+    that the buffers are first-touched on that node and the copy threads run next to it.  Without
+    this, ranks 4-7 of an 8-GPU box stage through the far socket (round 1: 42 -> 21 GB/s per GPU).
+    Returns a small record for the JSON line; any failure leaves the affinity untouched."""
+    info = {"gpu": index, "numa_node": None, "cpus": None}
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id",
+                              "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout
+        bus = out.strip().splitlines()[0].strip().lower()          # 00000000:1B:00.0
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)
+        with open(path) as fh:
+            node = int(fh.read().strip())
+        info["pci_bus_id"] = bus
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["numa_node"], info["cpus"] = node, len(allowed)
+    except Exception as exc:       # noqa: BLE001
+        info["error"] = "%s: %s" % (type(exc).__name__, exc)
+    return info
+
+
 def max_over_ranks(value, world, device="cpu"):
     """Job time = the slowest rank's device time (never a wall clock)."""
     if world == 1:
@@ -110,11 +149,13 @@ def parse_args():
     ap.add_argument("--width", type=int, default=624)
     ap.add_argument("--chunk", type=int, default=2,
                     help="samples handed to the SGA/LGA entry points per call")
+    ap.add_argument("--config", type=int, default=None, choices=[2, 3, 4],
+                    help="BASELINE.json config 2/3/4: the reference's models on the new operators "
+                         "(baseline/model_bench.py); default: the headline microbenchmark")
+    ap.add_argument("--per-gpu-batch", type=int, default=1, help="--config 2-4: samples per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0,
-                    help="target CPU time of the bounded cpu_baseline sample")
     return ap.parse_args()
 
 
@@ -183,9 +224,42 @@ class ClockSampler:
 
 
 # ---- the reference's CPU implementation (oracle/_ref, else the oracle port) -------
-def cpu_reference_rates(depth, height, width, seconds):
-    """Time SGA fwd+bwd and LGA2 fwd+bwd of the reference's own kernel bodies on the
-    host cores on a bounded sample; returns voxel rates and a description."""
+def physical_cores():
+    """Physical cores of the host (unique (package, core) pairs); falls back to os.cpu_count()."""
+    try:
+        seen, phys, core = set(), None, None
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("physical id"):
+                    phys = line.split(":")[1].strip()
+                elif line.startswith("core id"):
+                    core = line.split(":")[1].strip()
+                elif not line.strip():
+                    if phys is not None and core is not None:
+                        seen.add((phys, core))
+                    phys = core = None
+        if seen:
+            return len(seen)
+    except OSError:
+        pass
+    return os.cpu_count() or 1
+
+
+def pin_openmp_env():
+    """One OpenMP thread per physical core, bound (OMP_PLACES=cores, OMP_PROC_BIND=close): must be in
+    the environment before libgomp initialises, i.e. before numpy / the oracle libraries load.
+    Explicit user settings win."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(physical_cores()))
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+
+
+def cpu_reference_sample(depth, height, width):
+    """One bounded sample of the workload on the host cores with the reference's own kernel bodies
+    (oracle/_ref; the oracle port if the reference was not compiled here): SGA fwd+bwd on
+    (1, 2, D, H, W) -- the sample SURVEY.md 8d specifies: two full (n,c) slices, so the scan kernels
+    expose 2*H resp. 2*W lines to the host threads -- and LGA2 fwd+bwd on (1, D, H, W).  FIXED shapes
+    (no calibration), so every step and every box measures the same thing."""
     import numpy as np
     from oracle import api as port
     from oracle import ref_cpu
@@ -195,72 +269,44 @@ def cpu_reference_rates(depth, height, width, seconds):
     def l1(a, axis):
         return (a / np.abs(a).sum(axis=axis, keepdims=True)).astype(np.float32)
 
-    def sga_once(shape):
-        N, C, D, H, W = shape
-        x = rng.standard_normal(shape).astype(np.float32)
-        g = [l1(rng.standard_normal((N, C, 5, H, W)), 2) for _ in range(4)]
-        go = rng.standard_normal(shape).astype(np.float32)
-        t0 = time.perf_counter()
-        if use_ref:
-            out, mask, temp = ref_cpu.sga_forward(x, *g)
-            ref_cpu.sga_backward(x, *g, temp, mask, go)
-        else:
-            out, mask = port.sga_forward(x, *g, fused=False)
-            port.sga_backward(x, *g, mask, go, fused=False)
-        return time.perf_counter() - t0
-
-    def lga_once(shape):
-        x = rng.standard_normal(shape).astype(np.float32)
-        f = l1(rng.standard_normal((shape[0], 75) + shape[2:]), 1)
-        go = rng.standard_normal(shape).astype(np.float32)
-        t0 = time.perf_counter()
-        if use_ref:
-            y, y1 = ref_cpu.lga2_forward(x, f)
-            ref_cpu.lga2_backward(x, f, y1, go)
-        else:
-            y, tmp = port.lga_forward(x, f, 2, 2)
-            port.lga_backward(x, f, tmp, go, 2, 2)
-        return time.perf_counter() - t0
-
-    # calibrate on a thin slab of ONE (n,c) slice at the real D and W, then size the
-    # sample (rows of that slice) for ~seconds of CPU work.  The reference arm gets the
-    # thread count that serves it best: all logical CPUs or one per physical core.
-    cores = os.cpu_count() or 1
-    H, W = height, width
-    cal = (1, 1, depth, min(H, 16), W)
-    threads = cores
-    try:
-        import ctypes
-        gomp = ctypes.CDLL("libgomp.so.1")
-        sga_once(cal)                                   # warm the thread pool
-        best = None
-        for n in sorted({cores, max(1, cores // 2)}, reverse=True):
-            gomp.omp_set_num_threads(n)
-            t = min(sga_once(cal) for _ in range(2))
-            if best is None or t < best[0]:
-                best = (t, n)
-        threads = best[1]
-        gomp.omp_set_num_threads(threads)
-    except OSError:
-        pass
-    rate = np.prod(cal) / sga_once(cal)
-    hs = int(max(min(H, 16), min(H, rate * seconds * 0.6 / (depth * W))))
-    sga_shape = (1, 1, depth, hs, W)
-    t_sga = sga_once(sga_shape)
-    r_sga = float(np.prod(sga_shape) / t_sga)
-    lcal = (1, depth, min(H, 8), W)
-    lrate = np.prod(lcal) / lga_once(lcal)
-    hl = int(max(min(H, 8), min(H, lrate * seconds * 0.4 / (depth * W))))
-    lga_shape = (1, depth, hl, W)
-    t_lga = lga_once(lga_shape)
-    r_lga = float(np.prod(lga_shape) / t_lga)
+    cs = 2
+    while cs > 1 and cs * depth * height * width >= 2 ** 31:      # the reference indexes with int
+        cs -= 1
+    sga_shape = (1, cs, depth, height, width)
+    lga_shape = (1, depth, height, width)
+    N, C, D, H, W = sga_shape
+    x = rng.standard_normal(sga_shape).astype(np.float32)
+    g = [l1(rng.standard_normal((N, C, 5, H, W)), 2) for _ in range(4)]
+    go = rng.standard_normal(sga_shape).astype(np.float32)
+    t0 = time.perf_counter()
+    if use_ref:
+        out, mask, temp = ref_cpu.sga_forward(x, *g)
+        ref_cpu.sga_backward(x, *g, temp, mask, go)
+    else:
+        out, mask = port.sga_forward(x, *g, fused=False)
+        port.sga_backward(x, *g, mask, go, fused=False)
+    t_sga = time.perf_counter() - t0
+    del x, g, go, out, mask
+    xl = rng.standard_normal(lga_shape).astype(np.float32)
+    fl = l1(rng.standard_normal((1, 75) + lga_shape[2:]), 1)
+    gol = rng.standard_normal(lga_shape).astype(np.float32)
+    t0 = time.perf_counter()
+    if use_ref:
+        y, y1 = ref_cpu.lga2_forward(xl, fl)
+        ref_cpu.lga2_backward(xl, fl, y1, gol)
+    else:
+        y, tmp = port.lga_forward(xl, fl, 2, 2)
+        port.lga_backward(xl, fl, tmp, gol, 2, 2)
+    t_lga = time.perf_counter() - t0
     return {
-        "r_sga": r_sga, "r_lga": r_lga, "cores": cores,
-        "threads": threads,
+        "r_sga": float(np.prod(sga_shape) / t_sga), "r_lga": float(np.prod(lga_shape) / t_lga),
+        "t_sga": t_sga, "t_lga": t_lga, "cores": os.cpu_count() or 1,
+        "threads": int(os.environ.get("OMP_NUM_THREADS", "0")) or (os.cpu_count() or 1),
+        "omp": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OMP_PLACES", "OMP_PROC_BIND")},
         "kind": "reference" if use_ref else "port",
-        "sample": "SGA fwd+bwd on %s in %.1fs + LGA2 fwd+bwd on %s in %.1fs, rates combined in "
-                  "the workload's voxel proportions" % ("x".join(map(str, sga_shape)), t_sga,
-                                                       "x".join(map(str, lga_shape)), t_lga),
+        "sample": "SGA fwd+bwd on %s + LGA2 fwd+bwd on %s per step (fixed shapes), rates combined in "
+                  "the workload's voxel proportions" % ("x".join(map(str, sga_shape)),
+                                                       "x".join(map(str, lga_shape))),
     }
 
 
@@ -295,30 +341,35 @@ def combine_rates(v_sga, v_lga, r_sga, r_lga):
 
 def run_reference_arm(a):
     """`--impl reference`: the reference's own CPU implementation of the path on the
-    host cores, K bounded steps after W warm-ups.  Rank 0 only."""
+    host cores, K bounded steps after W warm-ups (each step = cpu_reference_sample).  Rank 0 only.
+    `value` is the MEDIAN step; `ms_per_step` is what one full-workload step would take at that rate
+    (an extrapolation, flagged), `measured_s_per_step` what a bounded step really took."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     B, C, D, H, W = a.batch, a.channels, a.depth, a.height, a.width
     v_sga, v_lga = B * C * D * H * W, B * D * H * W
-    per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
-    vals, info = [], None
+    vals, secs, info = [], [], None
     t_begin = time.perf_counter()
     for i in range(a.warmup + a.steps):
-        info = cpu_reference_rates(D, H, W, per_step)
+        info = cpu_reference_sample(D, H, W)
         if i >= a.warmup:
             vals.append(combine_rates(v_sga, v_lga, info["r_sga"], info["r_lga"]))
+            secs.append(info["t_sga"] + info["t_lga"])
     wall = time.perf_counter() - t_begin
-    value = statistics.mean(vals)
+    value = statistics.median(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * (v_sga + v_lga) / value, "higher_is_better": True,
+        "ms_per_step": 1e3 * (v_sga + v_lga) / value, "ms_per_step_extrapolated": True,
+        "measured_s_per_step": statistics.median(secs),
+        "value_min_max": [min(vals), max(vals)],
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "SGA+LGA2 fwd+bwd, B=%d C=%d D=%d HxW=%dx%d (CPU arm: bounded "
                                "sample per step)" % (B, C, D, H, W)},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": info["cores"],
-                         "threads": info["threads"], "kind": info["kind"],
+                         "threads": info["threads"], "omp": info["omp"], "kind": info["kind"],
                          "sample": info["sample"]},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -327,6 +378,26 @@ def run_reference_arm(a):
     }
     print(json.dumps(line))
     return 0
+
+
+def cpu_baseline_leg(a):
+    """The cpu_baseline object of our arm's line: the reference arm itself, in a child process so that
+    its OpenMP runtime starts with the pinned-thread environment (torch has already initialised
+    libgomp in this one), 1 warm-up + 2 bounded steps."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--batch", str(a.batch), "--channels", str(a.channels), "--depth", str(a.depth),
+           "--height", str(a.height), "--width", str(a.width)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        ref = json.loads(lines[-1])
+        out = dict(ref["cpu_baseline"])
+        out["measured_s_per_step"] = ref["measured_s_per_step"]
+        out["config1_cpu"] = ref.get("config1_cpu")
+        return out
+    except Exception as exc:       # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
 
 # ---- our arm ------------------------------------------------------------------------
@@ -363,6 +434,7 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     world, rank, local_rank = dist_setup("nccl", dev)
@@ -496,7 +568,7 @@ def run_ours(a):
                        "global_batch": B, "parallelism": "batch-shard x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2 (3.7 GB per sample, distinct per sample)",
                        "aggregates_kept_for_backward": bool(keep_flag[0])},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "numa": numa,
             "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (all launches of the call: scans + H<->W transposes + merge)",
                          "achieved": sga_gbs, "peak": peak, "unit": "GB/s",
                          "frac": sga_gbs / peak, "peak_source": peak_src,
@@ -507,11 +579,7 @@ def run_ours(a):
                                    "lga2_fwd": ph[2] / a.steps, "lga2_bwd": ph[3] / a.steps},
         }
         if world == 1 and not a.no_cpu_baseline:
-            info = cpu_reference_rates(D, H, W, a.cpu_seconds)
-            line["cpu_baseline"] = {
-                "value": combine_rates(v_sga, v_lga, info["r_sga"], info["r_lga"]),
-                "unit": "voxels/s", "cores": info["cores"], "threads": info["threads"],
-                "kind": info["kind"], "sample": info["sample"]}
+            line["cpu_baseline"] = cpu_baseline_leg(a)
         if world == 1 and not a.no_ref_gpu:
             del x, go
             torch.cuda.empty_cache()
@@ -675,7 +743,18 @@ def ref_gpu_rate(torch, dev, C, D, H, W):
 
 def main():
     a = parse_args()
+    if a.config is not None:
+        if a.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "config_id": a.config,
+                                  "unavailable": "the reference has no CPU path for its models; its CUDA "
+                                                 "kernels on this GPU are timed inside `--config %d` "
+                                                 "(reference_cuda_on_this_gpu)" % a.config}))
+            return 0
+        from baseline import model_bench
+        return model_bench.run(a)
     if a.impl == "reference":
+        pin_openmp_env()              # before numpy / libgomp load
         return run_reference_arm(a)
     return run_ours(a)
 

@@ -1,0 +1,139 @@
+"""BASELINE.json configs 2 and 3 on the GPU box: the reference's OWN models -- models/GANet11.py and
+models/GANet_deep.py, copied unmodified into baseline/_ref/models/ at build time -- run on the new
+operators through the drop-in `libs.GANet` / `libs.sync_bn` import surface, and the same model
+object with the same weights is run again with its hot-path modules switched to the UNMODIFIED
+reference CUDA extension (baseline/refops.py).
+
+  * every SGA call inside the model is checked bit-for-bit against the reference extension on the
+    very tensors the model feeds it (forward values bit-exact);
+  * every LGA2 / GetCostVolume / DisparityRegression call likewise, <= 1e-4 (exact for the copy);
+  * the disparity maps of the two runs agree <= 1e-4 relative, element-wise
+    (models/GANet_deep.py:389-410, models/GANet11.py:311-353).
+
+BatchNorm statistics: a freshly initialised model in eval mode has running_mean 0 / var 1, which lets
+activations grow through ~50 conv layers until the soft-argmin saturates; like a trained checkpoint
+would, the running statistics are therefore first set from one training-mode forward of the same
+input pair (momentum 1), then both runs use eval mode.
+"""
+import numpy as np
+import pytest
+import torch
+
+from baseline import refmodels, refops
+from oracle import ref_gpu
+from util import assert_close
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_gpu.available(), reason="reference CUDA extension not built"),
+              pytest.mark.skipif(not refmodels.available(), reason="reference models not copied")]
+
+
+def _calibrate_bn(model, left, right):
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    old = [m.momentum for m in bns]
+    for m in bns:
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(left, right)
+    for m, mo in zip(bns, old):
+        m.momentum = mo
+    model.eval()
+
+
+def _check_calls_against_reference(model, log):
+    """Forward hooks on the model's hot-path modules: each call's inputs go through the reference
+    implementation as well and the outputs are compared on the spot."""
+    import ganet_b200.modules as M
+    handles = []
+
+    def hook(mod, inputs, output):
+        inputs = [t.contiguous() for t in inputs]
+        if isinstance(mod, M.SGA):
+            ref = ref_gpu.sga_forward(*inputs)[0]
+            assert torch.equal(output, ref), "SGA output differs from the reference extension"
+            log.append(("SGA", tuple(output.shape)))
+        elif isinstance(mod, M.LGA2):
+            ref = ref_gpu.lga2_forward(*inputs)[0]
+            assert_close(output.cpu().numpy(), ref.cpu().numpy(), what="LGA2 inside the model")
+            log.append(("LGA2", tuple(output.shape)))
+        elif isinstance(mod, M.GetCostVolume):
+            assert torch.equal(output, refops.ref_cost_volume(inputs[0], inputs[1], mod.maxdisp))
+            log.append(("GetCostVolume", tuple(output.shape)))
+        else:
+            assert_close(output.cpu().numpy(), refops.ref_disp_regression(inputs[0]).cpu().numpy(),
+                         what="DisparityRegression inside the model")
+            log.append(("DisparityRegression", tuple(output.shape)))
+
+    for _, m in refops.hot_path_modules(model):
+        handles.append(m.register_forward_hook(hook))
+    return handles
+
+
+@pytest.mark.parametrize("name,H,W,n_sga", [("GANet11", 240, 624, 4), ("GANet_deep", 384, 1248, 7)])
+def test_reference_model_inference_on_new_operators(name, H, W, n_sga):
+    torch.backends.cudnn.benchmark = False
+    dev = torch.device("cuda:0")
+    model = refmodels.build(name, 192, seed=0, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    left = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    right = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    _calibrate_bn(model, left, right)
+
+    log = []
+    handles = _check_calls_against_reference(model, log)
+    with torch.no_grad():
+        d_new = model(left, right)
+    for h in handles:
+        h.remove()
+    assert d_new.shape == (1, H, W)
+    assert [k for k, _ in log].count("SGA") == n_sga
+    assert [k for k, _ in log].count("LGA2") == 2
+    assert [k for k, _ in log].count("GetCostVolume") == 1
+    assert [k for k, _ in log].count("DisparityRegression") == 1
+    sga_shapes = sorted({s for k, s in log if k == "SGA"})
+    assert sga_shapes == sorted({(1, 32, 65, H // 3, W // 3), (1, 48, 33, H // 6, W // 6)})
+
+    with refops.reference_ops(model), torch.no_grad():
+        d_ref = model(left, right)
+    a, b = d_new.cpu().numpy(), d_ref.cpu().numpy()
+    assert np.isfinite(b).all() and b.std() > 1e-3, "degenerate disparity map"
+    assert_close(a, b, what="%s disparity map, new operators vs reference extension" % name)
+
+
+def test_reference_model_training_step_on_new_operators():
+    """GANet-11 in training mode on a 96x192 crop (multiples of 48, README.md:63): the train.py loss
+    (:116-118, SceneFlow branch), the three disparity maps and the parameter gradients, new
+    operators vs reference extension from the same weights.  Gradients pass through ~40 layers of
+    cuDNN convolutions after the operators, so they are compared at 1e-3 of each tensor's scale."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.benchmark = False
+    dev = torch.device("cuda:0")
+    H, W = 96, 192
+    model = refmodels.build("GANet11", 192, seed=3, device=dev).train()
+    gen = torch.Generator(device=dev).manual_seed(4)
+    left = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    right = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    target = torch.rand(1, H, W, device=dev, generator=gen) * 191.0
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        disp1, disp2 = model(left, right)
+        loss = 0.4 * F.smooth_l1_loss(disp1, target) + 1.2 * F.smooth_l1_loss(disp2, target)
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        return loss.item(), disp1.detach().cpu().numpy(), disp2.detach().cpu().numpy(), grads
+
+    l_new, d1_new, d2_new, g_new = step()
+    with refops.reference_ops(model):
+        l_ref, d1_ref, d2_ref, g_ref = step()
+    assert abs(l_new - l_ref) <= 1e-4 * abs(l_ref)
+    assert_close(d1_new, d1_ref, what="disp1")
+    assert_close(d2_new, d2_ref, what="disp2")
+    assert set(g_new) == set(g_ref) and len(g_new) >= 180
+    worst = 0.0
+    for n in g_ref:
+        a, b = g_new[n].cpu().numpy(), g_ref[n].cpu().numpy()
+        scale = max(float(np.abs(b).max()), 1e-30)
+        worst = max(worst, float(np.abs(a - b).max()) / scale)
+    assert worst <= 1e-3, "parameter gradients differ: worst relative error %.3g" % worst

@@ -47,7 +47,10 @@ SGA_SHAPES = [(2, 3, 7, 5, 6), (1, 2, 1, 4, 3), (1, 1, 2, 1, 5), (1, 2, 3, 6, 1)
               # H and W multiples of 16: the TMA-staged kernels run in both layouts; partial
               # 32-column strips (48, 80), depth not filling the last warp (65, 33), one stage
               (1, 2, 24, 16, 48), (2, 2, 65, 32, 80), (1, 1, 192, 16, 32), (1, 2, 33, 16, 16),
-              (1, 1, 256, 16, 16)]
+              (1, 1, 256, 16, 16),
+              # D > 288: the generic line kernels (sga_forward_lines / sga_backward_lines) carry the
+              # whole call -- MODE_FIRST / MODE_COMBINE and the vertical line-kernel backward
+              (1, 1, 300, 4, 6), (1, 2, 513, 3, 5)]
 
 
 @needs_ref
@@ -366,6 +369,99 @@ def test_disparity_regression_vs_torch(shape):
     out.backward(g)
     ref.backward(g)
     assert torch.equal(p.grad, p2.grad)
+
+
+@pytest.mark.parametrize("shape,dm", [((1, 32, 80, 208), 65), ((1, 32, 128, 416), 65)])
+def test_cost_volume_at_model_shapes(shape, dm):
+    """GetCostVolume at the shapes GANet-11 (240x624) and GANet-deep (384x1248) feed it
+    (models/GANet_deep.py:399): bit-exact forward, gradients vs the reference's slice-assign autograd.
+    Prints device time and algorithmic DRAM bytes (profiles/r02_volume_ops.txt is this output)."""
+    from ganet_b200.modules import GetCostVolume
+    torch.manual_seed(2)
+    x = torch.randn(shape, device="cuda", requires_grad=True)
+    y = torch.randn(shape, device="cuda", requires_grad=True)
+    mod = GetCostVolume(dm - 1)
+    cost = mod(x, y)
+    x2, y2 = x.detach().clone().requires_grad_(), y.detach().clone().requires_grad_()
+    ref = _ref_cost_volume(x2, y2, dm)
+    assert torch.equal(cost, ref)
+    gc = torch.randn_like(cost)
+    cost.backward(gc)
+    ref.backward(gc)
+    assert_close(npy(x.grad), npy(x2.grad), RTOL, "grad_x")
+    assert_close(npy(y.grad), npy(y2.grad), RTOL, "grad_y")
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    with torch.no_grad():
+        mod(x, y)
+    e[0].record()
+    for _ in range(10):
+        c = mod(x, y)
+    e[1].record()
+    for _ in range(10):
+        torch.autograd.grad(c, (x, y), gc, retain_graph=True)
+    e[2].record()
+    torch.cuda.synchronize()
+    nb = cost.numel() * 4
+    print("\nGetCostVolume %s dm=%d: fwd %.3f ms (%.0f GB/s of %d MB written), bwd %.3f ms (%.0f GB/s read)"
+          % (shape, dm, e[0].elapsed_time(e[1]) / 10, nb / (e[0].elapsed_time(e[1]) / 10) / 1e6, nb >> 20,
+             e[1].elapsed_time(e[2]) / 10, nb / (e[1].elapsed_time(e[2]) / 10) / 1e6))
+
+
+@pytest.mark.parametrize("shape", [(1, 193, 240, 624), (1, 193, 384, 1248)])
+def test_disparity_regression_at_model_shapes(shape):
+    """DisparityRegression at full resolution (models/GANet_deep.py:219,247), forward and backward,
+    against the reference's repeat * sum lines; prints device time and achieved bandwidth."""
+    from ganet_b200.modules import DisparityRegression
+    torch.manual_seed(3)
+    p = torch.softmax(torch.randn(shape, device="cuda"), 1).requires_grad_()
+    mod = DisparityRegression(shape[1] - 1)
+    out = mod(p)
+    disp = torch.arange(shape[1], device="cuda", dtype=torch.float32).reshape(1, -1, 1, 1)
+    disp = disp.repeat(p.size()[0], 1, p.size()[2], p.size()[3])
+    p2 = p.detach().clone().requires_grad_()
+    ref = torch.sum(p2 * disp, 1)
+    assert_close(npy(out), npy(ref), RTOL, "disparity")
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g)
+    assert torch.equal(p.grad, p2.grad)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    for _ in range(10):
+        o = mod(p)
+    e[1].record()
+    for _ in range(10):
+        torch.autograd.grad(o, p, g, retain_graph=True)
+    e[2].record()
+    torch.cuda.synchronize()
+    nb = p.numel() * 4
+    print("\nDisparityRegression %s: fwd %.3f ms (%.0f GB/s of %d MB read), bwd %.3f ms (%.0f GB/s written)"
+          % (shape, e[0].elapsed_time(e[1]) / 10, nb / (e[0].elapsed_time(e[1]) / 10) / 1e6, nb >> 20,
+             e[1].elapsed_time(e[2]) / 10, nb / (e[1].elapsed_time(e[2]) / 10) / 1e6))
+
+
+@needs_ref
+@pytest.mark.parametrize("fname,passes", [("LgaFunction", 1), ("Lga3Function", 3), ("Lga3d3Function", 3)])
+def test_lga_1_and_3_pass_functions_through_autograd(fname, passes):
+    """LgaFunction / Lga3Function (broken upstream: functions/GANet.py:155,241-242) and Lga3d3Function
+    through torch.autograd on the GPU, against `passes` chained calls of the reference extension's
+    lga_cuda_forward / backward with its accumulate-into-gradFilters contract."""
+    import ganet_b200.functions as Fn
+    fn = getattr(Fn, fname)
+    shape = (1, 2, 6, 9, 12) if "3d" in fname else (2, 6, 9, 12)
+    x, f, go = lga_inputs(shape, seed=21 + passes)
+    xt, ft = cu(x).requires_grad_(), cu(f).requires_grad_()
+    y = fn.apply(xt, ft, 2)
+    y.backward(cu(go))
+    xs = [cu(x)]
+    for _ in range(passes):
+        xs.append(ref_gpu.lga_forward(xs[-1], cu(f), 2))
+    assert_close(npy(y), npy(xs[-1]), RTOL, fname + " output")
+    g, gf = cu(go), None
+    for k in range(passes - 1, -1, -1):
+        g, gf = ref_gpu.lga_backward(xs[k], cu(f), g, gf, 2)
+    assert_close(npy(xt.grad), npy(g), RTOL, fname + " grad_x")
+    assert_close(npy(ft.grad), npy(gf), RTOL, fname + " grad_filters")
 
 
 # ---- autograd / API behaviour -----------------------------------------------------
