@@ -26,6 +26,7 @@ _SIGNATURES = {
     "ganet_sga_forward_workspace_best": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_min": (_sz, [_i64] * 5),
     "ganet_sga_backward_workspace_best": (_sz, [_i64] * 5),
+    "ganet_sga_aggregate_volumes": (_int, [_i64] * 5),
     "ganet_sga_backward": (_int, [_vp] * 15 + [_sz] + [_i64] * 5 + [_vp]),
     "ganet_sga_direction": (_int, [_vp] * 3 + [_int] + [_i64] * 5 + [_vp]),
     "ganet_lga_forward": (_int, [_vp] * 3 + [_i64] * 4 + [_int, _vp]),

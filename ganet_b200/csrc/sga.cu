@@ -32,6 +32,7 @@
 #include "sga_step.cuh"
 #include "sga_vert.cuh"
 #include "sga_tma.cuh"
+#include "sga_hscan.cuh"
 #include "transpose.cuh"
 
 namespace ganet {
@@ -656,6 +657,132 @@ static int launch_tma_hraw(VCfg c, const float *x, const float *g, float *out, i
     return GANET_OK;
 }
 
+
+// ---- horizontal scans in the standard layout (sga_hscan.cuh) ---------------------------------
+// K = depths per lane (even), 32 lanes cover D <= 32*K; the TMA box holds all D planes (<= 256).
+#define GANET_HSCAN_KS(X) X(2) X(4) X(6) X(8)
+
+static bool hscan_enabled()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("GANET_NO_HSCAN") ? 0 : 1;
+    return v != 0 && tma_enabled();
+}
+
+static int hscan_k(int D)
+{
+    for (int k = 2; k <= 8; k += 2)
+        if (32 * k >= D) return k;
+    return 0;
+}
+
+// Shapes the horizontal kernels take: every tensor row 16-byte aligned for fp32 AND for the uint8
+// mask (W % 16 == 0), all planes of a slice in one TMA box (D <= 256).  A pure function of the
+// shape (plus the process-wide switches), so forward and backward agree on the layout of the kept
+// aggregates without passing a flag.
+static bool hscan_ok(int D, int H, int W)
+{
+    (void)H;
+    return hscan_enabled() && D <= 256 && (W % 16) == 0 && get_encode_tiled() != nullptr;
+}
+
+constexpr int kHscanCtaBudget = 110 * 1024;       // two CTAs per SM
+
+template <int DIR>
+static int launch_hscan_fwd(const float *x, const float *g, float *out, int D, int H, int W,
+                            long long n_slices, cudaStream_t st)
+{
+    constexpr int BW = 32;
+    const int K = hscan_k(D);
+    if (!K || D > 256 || (W % 4) != 0) return kNotApplicable;
+    const int stage = hfwd_stage_bytes(D, BW);
+    const int nb = (W + BW - 1) / BW;
+    int S = (kHscanCtaBudget - 2048) / stage;
+    if (S > 8) S = 8;
+    if (S > nb) S = nb;
+    if (S < 2 && nb >= 2) return kNotApplicable;
+    if (S < 1) S = 1;
+    const size_t smem = (size_t)S * stage + 2 * S * sizeof(uint64_t) + 1024;      // + alignment slack
+    HFwdMaps maps;
+    if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, BW, D, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return kNotApplicable;
+    if (!make_plane_map(&maps.out, out, 4, n_slices * D, H, W, BW, D, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return kNotApplicable;
+    if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, BW, 5, 1)) return kNotApplicable;
+    const long long blocks = n_slices * H;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const bool full = (32 * K == D);
+#define X(K_)                                                                                  \
+    if (K == K_) {                                                                             \
+        auto kf = sga_hscan_fwd_kernel<K_, BW, DIR, true>;                                     \
+        auto kp = sga_hscan_fwd_kernel<K_, BW, DIR, false>;                                    \
+        auto k = full ? kf : kp;                                                               \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+            cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
+        k<<<(unsigned)blocks, 64, smem, st>>>(maps, D, H, W, S);                               \
+    } else
+    GANET_HSCAN_KS(X) { return kNotApplicable; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+template <int DIR>
+static int launch_hscan_bwd(const float *x, const float *g, const float *a, const uint8_t *mask,
+                            const float *go, float *gi, float *gg, int32_t *max_idx, int mask_id,
+                            int accumulate, int D, int H, int W, long long n_slices, cudaStream_t st)
+{
+    constexpr int BW = 16;
+    const int K = hscan_k(D);
+    if (!K || D > 256 || (W % 16) != 0) return kNotApplicable;
+    const HBwdPlan pl = hbwd_plan(D, BW);
+    const int nb = (W + BW - 1) / BW;
+    int S = (kHscanCtaBudget - 2048) / pl.stage_bytes;
+    if (S > 4) S = 4;
+    if (S > nb) S = nb;
+    if (S < 2 && nb >= 2) return kNotApplicable;
+    if (S < 1) S = 1;
+    const size_t smem = (size_t)S * pl.stage_bytes + 2 * S * sizeof(uint64_t) + 1024;
+    HBwdMaps maps;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
+    if (!make_plane_map(&maps.go, go, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
+    if (!make_plane_map(&maps.a, a, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
+    if (!make_plane_map(&maps.gi, gi, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
+    if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, BW, D, 1, CU_TENSOR_MAP_SWIZZLE_32B)) return kNotApplicable;
+    if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, BW, 5, 1)) return kNotApplicable;
+    const long long blocks = n_slices * H;
+    if (blocks <= 0) return GANET_OK;
+    if (blocks > 0x7fffffffll) return GANET_EUNSUPPORTED;
+    const bool full = (32 * K == D);
+#define X(K_)                                                                                  \
+    if (K == K_) {                                                                             \
+        auto kf = sga_hscan_bwd_kernel<K_, BW, DIR, true>;                                     \
+        auto kp = sga_hscan_bwd_kernel<K_, BW, DIR, false>;                                    \
+        auto k = full ? kf : kp;                                                               \
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+            cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
+        k<<<(unsigned)blocks, 64, smem, st>>>(maps, gg, max_idx, mask_id, accumulate, D, H, W, S); \
+    } else
+    GANET_HSCAN_KS(X) { return kNotApplicable; }
+#undef X
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+static int launch_merge4(const float *a0, const float *a1, const float *a2, const float *a3, float *out,
+                         uint8_t *mask, long long total, cudaStream_t st)
+{
+    if (total % 4) return GANET_EUNSUPPORTED;
+    const long long n4 = total / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks <= 0) return GANET_OK;
+    merge4_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float4 *)a0, (const float4 *)a1, (const float4 *)a2,
+                                                    (const float4 *)a3, (float4 *)out, (uint32_t *)mask, n4);
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
 // Should the transpose-free forward (hraw x2 + FIRST3 + COMBINE, 4 launches instead of 9) run?
 // Its boxes have a 16-byte inner extent: 6144 tiny TMA requests per box, which is request-rate
 // bound once the volume no longer sits in L2.  Measured on B200 (profiles/): faster up to
@@ -710,9 +837,16 @@ using namespace ganet;
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct FwdWs { size_t xT, outT, maskT, t3, gT2, gT3, total; };
-static FwdWs fwd_ws(long long n, long long S, long long HW, bool keep = false)
+static FwdWs fwd_ws(long long n, long long S, long long HW, bool keep = false, bool hs = false)
 {
     FwdWs w; size_t o = 0;
+    if (hs) {       // horizontal scans in the standard layout: two aggregates of scratch unless kept
+        w.xT = o;    o += keep ? 0 : align_up((size_t)n * S * 4);
+        w.outT = o;  o += keep ? 0 : align_up((size_t)n * S * 4);
+        w.maskT = w.t3 = w.gT2 = w.gT3 = o;
+        w.total = o ? o : 256;
+        return w;
+    }
     // keep: xT and the aggregates live in the caller's buffer; only the guidance is staged here
     w.xT = o;    o += keep ? 0 : align_up((size_t)n * S * 4);
     w.outT = o;  o += keep ? 0 : align_up((size_t)n * S * 4);
@@ -725,9 +859,15 @@ static FwdWs fwd_ws(long long n, long long S, long long HW, bool keep = false)
 }
 
 struct BwdWs { size_t a, xT, goT, maskT, giT, gT, ggT, total; };
-static BwdWs bwd_ws(long long n, long long S, long long HW, bool kept = false)
+static BwdWs bwd_ws(long long n, long long S, long long HW, bool kept = false, bool hs = false)
 {
     BwdWs w; size_t o = 0;
+    if (hs) {       // only the recompute variant needs scratch: one aggregate at a time
+        w.a = o;     o += kept ? 0 : align_up((size_t)n * S * 4);
+        w.xT = w.goT = w.maskT = w.giT = w.gT = w.ggT = o;
+        w.total = o ? o : 256;
+        return w;
+    }
     w.a = o;     o += kept ? 0 : align_up((size_t)n * S * 4);    // kept aggregates: no recompute scratch
     w.xT = o;    o += kept ? 0 : align_up((size_t)n * S * 4);    // ... and xT is kept as well
     w.goT = o;   o += align_up((size_t)n * S * 4);
@@ -755,22 +895,33 @@ static long long fit_slices(F sizer, size_t bytes, long long ns)
 GANET_API size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
     (void)N; (void)C;
-    const size_t a = fwd_ws(1, D * H * W, H * W, false).total, b = fwd_ws(1, D * H * W, H * W, true).total;
+    const bool hs = hscan_ok((int)D, (int)H, (int)W);
+    const size_t a = fwd_ws(1, D * H * W, H * W, false, hs).total, b = fwd_ws(1, D * H * W, H * W, true, hs).total;
     return a > b ? a : b;          // one size serves both forward variants (the plain one is larger)
 }
 GANET_API size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
-    const size_t a = fwd_ws(N * C, D * H * W, H * W, false).total, b = fwd_ws(N * C, D * H * W, H * W, true).total;
+    const bool hs = hscan_ok((int)D, (int)H, (int)W);
+    const size_t a = fwd_ws(N * C, D * H * W, H * W, false, hs).total, b = fwd_ws(N * C, D * H * W, H * W, true, hs).total;
     return a > b ? a : b;
 }
 GANET_API size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
     (void)N; (void)C;
-    return bwd_ws(1, D * H * W, H * W).total;
+    return bwd_ws(1, D * H * W, H * W, false, hscan_ok((int)D, (int)H, (int)W)).total;
 }
 GANET_API size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
 {
-    return bwd_ws(N * C, D * H * W, H * W).total;
+    return bwd_ws(N * C, D * H * W, H * W, false, hscan_ok((int)D, (int)H, (int)W)).total;
+}
+
+/* How many (N,C,D,H,W) volumes the `aggregates` buffer of ganet_sga_forward / _backward holds for
+ * this shape: 4 (the four aggregates, standard layout) when the horizontal scans run in the standard
+ * layout, 5 (down, up, right^T, left^T, x^T) on the transposed path. */
+GANET_API int ganet_sga_aggregate_volumes(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W)
+{
+    (void)N; (void)C;
+    return hscan_ok((int)D, (int)H, (int)W) ? 4 : 5;
 }
 
 // slow generic path: one warp group per scan line, any D <= 768, no workspace
@@ -806,14 +957,41 @@ GANET_API int ganet_sga_forward(const float *x, const float *g_down, const float
         return sga_forward_lines(x, g, out, mask, (int)D, (int)H, (int)W, ns, st);
     }
     const bool keep = aggregates != nullptr;
+    const int iD = (int)D, iH = (int)H, iW = (int)W;
+    const bool hs = hscan_ok(iD, iH, iW);
     const long long chunk = workspace
-        ? fit_slices([&](long long n) { return fwd_ws(n, S, HW, keep).total; }, workspace_bytes, ns) : 0;
+        ? fit_slices([&](long long n) { return fwd_ws(n, S, HW, keep, hs).total; }, workspace_bytes, ns) : 0;
     if (chunk < 1) return GANET_EWORKSPACE;
     char *ws = (char *)workspace;
-    const int iD = (int)D, iH = (int)H, iW = (int)W;
     for (long long s0 = 0; s0 < ns; s0 += chunk) {
         const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
-        const FwdWs w = fwd_ws(n, S, HW, keep);
+        const FwdWs w = fwd_ws(n, S, HW, keep, hs);
+        if (hs) {
+            // Horizontal scans in the standard layout (sga_hscan.cuh): no transposes anywhere.
+            const float *xs = x + s0 * S;
+            float *os = out + s0 * S;
+            uint8_t *ms = mask + s0 * S;
+            if (keep) {
+                // the four raw aggregates go to the caller's buffer, one streaming kernel merges them
+                float *A[4];
+                for (int k = 0; k < 4; k++) A[k] = aggregates + k * ns * S + s0 * S;
+                if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_down + s0 * 5 * HW, A[0], nullptr, 0, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+                if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, g_up + s0 * 5 * HW, A[1], nullptr, 1, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+                if ((rc = launch_hscan_fwd<0>(xs, g_right + s0 * 5 * HW, A[2], iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                if ((rc = launch_hscan_fwd<1>(xs, g_left + s0 * 5 * HW, A[3], iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                if ((rc = launch_merge4(A[0], A[1], A[2], A[3], os, ms, n * S, st))) return rc;
+                continue;
+            }
+            // recompute variant: right and left aggregates into scratch, `down` merges all three
+            // (strict <, lower id wins), `up` merges on top
+            float *a2 = (float *)(ws + w.xT), *a3 = (float *)(ws + w.outT);
+            if ((rc = launch_hscan_fwd<0>(xs, g_right + s0 * 5 * HW, a2, iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+            if ((rc = launch_hscan_fwd<1>(xs, g_left + s0 * 5 * HW, a3, iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+            rc = launch_tma_fwd<VMODE_FIRST3>(vc, xs, g_down + s0 * 5 * HW, os, ms, 0, MaskIds{0, 0}, iD, iH, iW, n, st, a2, a3);
+            if (rc) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;   // D <= 256 always fits two stages
+            if ((rc = run_vert_fwd<VMODE_COMBINE>(vc, xs, g_up + s0 * 5 * HW, os, ms, 1, MaskIds{0, 1}, iD, iH, iW, n, st))) return rc;
+            continue;
+        }
         if (keep) {
             // Memory-for-bandwidth variant: every direction's raw aggregate goes to the caller's
             // buffer (down, up in the standard layout; right, left transposed -- the layouts
@@ -883,6 +1061,11 @@ GANET_API int ganet_sga_direction(const float *x, const float *g, float *a, int 
     if (dir < 2 && pick_vert_cfg((int)D, &vc))
         return run_vert_fwd<VMODE_RAW>(vc, x, g, a, nullptr, dir, MaskIds{0, 0}, (int)D, (int)H,
                                           (int)W, N * C, (cudaStream_t)stream);
+    if (dir >= 2 && hscan_ok((int)D, (int)H, (int)W)) {
+        rc = dir == 2 ? launch_hscan_fwd<0>(x, g, a, (int)D, (int)H, (int)W, N * C, (cudaStream_t)stream)
+                      : launch_hscan_fwd<1>(x, g, a, (int)D, (int)H, (int)W, N * C, (cudaStream_t)stream);
+        if (rc != kNotApplicable) return rc;
+    }
     if (!pick_cfg((int)D, dir < 2, &c)) return GANET_EUNSUPPORTED;
     return launch_fwd<MODE_RAW>(c, x, g, a, nullptr, dir, (int)D, (int)H, (int)W, N * C,
                                 (cudaStream_t)stream);
@@ -941,13 +1124,43 @@ GANET_API int ganet_sga_backward(const float *x, const float *g_down, const floa
                                   fit < ns ? fit : ns, iD, iH, iW, ns, st);
     }
     const bool kept = aggregates != nullptr;     // forward kept the four aggregates: no recompute
+    const bool hs = hscan_ok(iD, iH, iW);
     const long long chunk =
-        fit_slices([&](long long n) { return bwd_ws(n, S, HW, kept).total; }, workspace_bytes, ns);
+        fit_slices([&](long long n) { return bwd_ws(n, S, HW, kept, hs).total; }, workspace_bytes, ns);
     if (chunk < 1) return GANET_EWORKSPACE;
     char *ws = (char *)workspace;
     for (long long s0 = 0; s0 < ns; s0 += chunk) {
         const long long n = (ns - s0 < chunk) ? ns - s0 : chunk;
-        const BwdWs w = bwd_ws(n, S, HW, kept);
+        const BwdWs w = bwd_ws(n, S, HW, kept, hs);
+        if (hs) {
+            // all four reverse sweeps in the standard layout; gradInput: `down` stores, the other
+            // three accumulate with TMA reduce-adds
+            float *a = (float *)(ws + w.a);
+            const float *xs = x + s0 * S, *gos = grad_out + s0 * S;
+            const uint8_t *ms = mask + s0 * S;
+            float *gis = grad_in + s0 * S;
+            for (int dir = 0; dir < 4; dir++) {
+                const float *gd = g[dir] + s0 * 5 * HW;
+                float *ggd = gg[dir] + s0 * 5 * HW;
+                const float *ak = kept ? aggregates + dir * ns * S + s0 * S : a;
+                if (dir < 2) {
+                    if (!kept)
+                        if ((rc = run_vert_fwd<VMODE_RAW>(vc, xs, gd, a, nullptr, dir, MaskIds{0, 0}, iD, iH, iW, n, st))) return rc;
+                    if ((rc = run_vert_bwd(vc, xs, gd, ak, ms, gos, gis, ggd, dir, dir, dir > 0, iD, iH, iW, n, st))) return rc;
+                } else if (dir == 2) {
+                    if (!kept)
+                        if ((rc = launch_hscan_fwd<0>(xs, gd, a, iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                    rc = launch_hscan_bwd<0>(xs, gd, ak, ms, gos, gis, ggd, max_idx ? max_idx + s0 * HW : nullptr, 2, 1, iD, iH, iW, n, st);
+                    if (rc) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                } else {
+                    if (!kept)
+                        if ((rc = launch_hscan_fwd<1>(xs, gd, a, iD, iH, iW, n, st))) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                    rc = launch_hscan_bwd<1>(xs, gd, ak, ms, gos, gis, ggd, nullptr, 3, 1, iD, iH, iW, n, st);
+                    if (rc) return rc == kNotApplicable ? GANET_EUNSUPPORTED : rc;
+                }
+            }
+            continue;
+        }
         float *a = (float *)(ws + w.a), *xT = (float *)(ws + w.xT), *goT = (float *)(ws + w.goT);
         float *giT = (float *)(ws + w.giT), *gT = (float *)(ws + w.gT), *ggT = (float *)(ws + w.ggT);
         uint8_t *maskT = (uint8_t *)(ws + w.maskT);

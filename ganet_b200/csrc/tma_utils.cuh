@@ -151,7 +151,8 @@ static inline PFN_encodeTiled get_encode_tiled()
 // (dim0 = W contiguous, dim1 = H, dim2 = planes); box = (box_w, box_h, box_planes).
 // Returns false if the shape violates a TMA constraint (caller falls back).
 static inline bool make_plane_map(CUtensorMap *map, const void *base, int elem, long long planes, int H,
-                                  int W, int box_w, int box_planes, int box_h = 1)
+                                  int W, int box_w, int box_planes, int box_h = 1,
+                                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE)
 {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
@@ -164,7 +165,7 @@ static inline bool make_plane_map(CUtensorMap *map, const void *base, int elem, 
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                      const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }

@@ -64,7 +64,8 @@ def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None, keep_aggregates=False):
         dims = _dims5(x)
         ws, ws_bytes = _workspace(x, L.ganet_sga_forward_workspace_min(*dims),
                                   L.ganet_sga_forward_workspace_best(*dims), workspace_bytes)
-        agg = torch.empty((5, x.numel()), dtype=x.dtype, device=x.device) if keep_aggregates else None
+        agg = (torch.empty((L.ganet_sga_aggregate_volumes(*dims), x.numel()), dtype=x.dtype, device=x.device)
+               if keep_aggregates else None)
         check(L.ganet_sga_forward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3), ptr(out),
                                   ptr(mask, torch.uint8), ptr(agg) if agg is not None else None,
                                   ptr(ws, torch.uint8), _lib._sz(ws_bytes), *dims, stream()))
@@ -97,8 +98,8 @@ def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspac
         dims = _dims5(x)
         ws, ws_bytes = _workspace(x, L.ganet_sga_backward_workspace_min(*dims),
                                   L.ganet_sga_backward_workspace_best(*dims), workspace_bytes)
-        if aggregates is not None and tuple(aggregates.shape) != (5, x.numel()):
-            raise ValueError("aggregates must be the (5, x.numel()) tensor returned by sga_forward")
+        if aggregates is not None and tuple(aggregates.shape) != (L.ganet_sga_aggregate_volumes(*dims), x.numel()):
+            raise ValueError("aggregates must be the tensor returned by sga_forward(keep_aggregates=True)")
         check(L.ganet_sga_backward(ptr(x), ptr(g0), ptr(g1), ptr(g2), ptr(g3),
                                    ptr(mask, torch.uint8),
                                    ptr(aggregates) if aggregates is not None else None,

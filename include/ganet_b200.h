@@ -66,12 +66,13 @@ const char *ganet_error_string(int code);
  *       L1-normalised them over dim 2 (models/GANet_deep.py:265-268)
  *   mask   : (N, C, D, H, W) uint8, winning direction 0=down 1=up 2=right
  *       3=left, ties keep the lower id (GANet_kernel.cu:23-36)
- *   aggregates : optional (may be NULL).  5 * N*C*D*H*W floats that receive the four
- *       directional aggregates -- down, up as (N,C,D,H,W); right, left TRANSPOSED as
- *       (N,C,D,W,H) -- and the H<->W transposed input, for ganet_sga_backward, which
- *       then skips its four recompute passes and one transpose (-20 % SGA time for
- *       forward+backward; +20 bytes per voxel of saved state -- the reference saves 8:
- *       temp_out and an fp32 mask, functions/GANet.py:21).  Needs D <= 288.
+ *   aggregates : optional (may be NULL).  ganet_sga_aggregate_volumes(...) * N*C*D*H*W
+ *       floats that receive the four directional aggregates for ganet_sga_backward, which
+ *       then skips its four recompute passes: 4 volumes, all (N,C,D,H,W), when the
+ *       horizontal scans run in the standard layout (D <= 256, W % 16 == 0); otherwise 5
+ *       -- down, up as (N,C,D,H,W), right, left TRANSPOSED as (N,C,D,W,H), and the H<->W
+ *       transposed input.  +16 / +20 bytes per voxel of saved state -- the reference saves
+ *       8: temp_out and an fp32 mask, functions/GANet.py:21.  Needs D <= 288.
  *   workspace : device scratch (transposed copies for the horizontal scans),
  *       >= ganet_sga_forward_workspace_min bytes; the (n,c) slices are processed
  *       in chunks that fit, so any size between _min and _best works
@@ -90,6 +91,10 @@ size_t ganet_sga_forward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t 
 size_t ganet_sga_forward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 size_t ganet_sga_backward_workspace_min(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 size_t ganet_sga_backward_workspace_best(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
+
+/* Volumes of N*C*D*H*W floats the optional `aggregates` buffer must hold for this shape (4 or
+ * 5, see ganet_sga_forward).  No reference counterpart: the reference keeps temp_out + mask. */
+int ganet_sga_aggregate_volumes(int64_t N, int64_t C, int64_t D, int64_t H, int64_t W);
 
 /*
  * Replaces sga_cuda_backward (GANet_cuda.cpp:50-64 -> sga_kernel_backward,

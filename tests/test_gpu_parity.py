@@ -152,10 +152,16 @@ def test_kept_aggregates_give_identical_results(ops, shape):
     assert torch.equal(out, out3) and torch.equal(mask, mask3) and torch.equal(agg, agg3)
     for d in (0, 1):
         assert torch.equal(agg[d].view_as(xt), ops.sga_direction(xt, gt[d], d))
-    for d in (2, 3):
-        a = ops.sga_direction(xt, gt[d], d)
-        assert torch.equal(agg[d].view(*shape[:3], shape[4], shape[3]), a.transpose(3, 4).contiguous())
-    assert torch.equal(agg[4].view(*shape[:3], shape[4], shape[3]), xt.transpose(3, 4).contiguous())
+    if agg.shape[0] == 4:        # horizontal scans in the standard layout (W % 16 == 0, D <= 256)
+        assert shape[4] % 16 == 0
+        for d in (2, 3):
+            assert torch.equal(agg[d].view_as(xt), ops.sga_direction(xt, gt[d], d))
+    else:                        # transposed path: right^T, left^T, x^T
+        assert agg.shape[0] == 5
+        for d in (2, 3):
+            a = ops.sga_direction(xt, gt[d], d)
+            assert torch.equal(agg[d].view(*shape[:3], shape[4], shape[3]), a.transpose(3, 4).contiguous())
+        assert torch.equal(agg[4].view(*shape[:3], shape[4], shape[3]), xt.transpose(3, 4).contiguous())
     ref = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True)
     for wsb in (None, 1):
         got2 = ops.sga_backward(xt, *gt, mask, got, want_max_idx=True, aggregates=agg, workspace_bytes=wsb)
@@ -196,13 +202,17 @@ def test_sga_against_golden_vectors(ops):
             assert_close(npy(gg[d]), z[f"gg{k}_{d}"], RTOL, "guidance grad")
 
 
-def test_tma_and_ldg_kernels_agree_bitwise(ops):
-    """GANET_NO_TMA is read once per process, so compare through a subprocess: the plain
-    load/store kernels and the TMA-staged ones must give identical bits."""
+def test_tma_and_ldg_kernels_agree_bitwise(ops, tmp_path):
+    """The code paths behind the process-wide switches (read once per process, hence subprocesses):
+    horizontal scans in the standard layout (default), the H<->W transposed TMA path with and without
+    its transpose-free small-call forward, the plain load/store kernels, and gradInput accumulated by
+    TMA reduce-add or by load + add + store.  `out` and `mask` must be the same bits on every path;
+    the transposed-family paths must also agree bit for bit on every gradient (same summation order),
+    and the standard-layout path -- which sums over depth inside one warp -- within 1e-4."""
     import subprocess
     import sys
     code = (
-        "import sys, torch, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+        "import sys, torch, hashlib, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r);"
         "from ganet_b200 import ops; from util import sga_inputs;"
         "x, g, go = sga_inputs((1, 2, 24, 32, 48), seed=77);"
         "cu = lambda a: torch.from_numpy(a).cuda();"
@@ -210,22 +220,31 @@ def test_tma_and_ldg_kernels_agree_bitwise(ops):
         "out, mask = ops.sga_forward(xt, *gt);"
         "gi, gg = ops.sga_backward(xt, *gt, mask, cu(go));"
         "h = hashlib.sha256();"
-        "[h.update(t.cpu().numpy().tobytes()) for t in (out, mask, gi) + tuple(gg)];"
-        "print(h.hexdigest())"
+        "[h.update(t.cpu().numpy().tobytes()) for t in (out, mask)];"
+        "h2 = hashlib.sha256();"
+        "[h2.update(t.cpu().numpy().tobytes()) for t in (gi,) + tuple(gg)];"
+        "np.savez(sys.argv[1], gi=gi.cpu().numpy(), **{'gg%%d' %% k: t.cpu().numpy() for k, t in enumerate(gg)});"
+        "print(h.hexdigest(), h2.hexdigest())"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    digests = []
-    # default (TMA + transpose-free forward for small calls), transposed TMA path, plain LDG kernels
-    # ... and gradInput accumulated by TMA reduce-add instead of load + add + store
-    for knobs in ({}, {"GANET_NO_DIRECT": "1"}, {"GANET_NO_TMA": "1"}, {"GANET_TMA_REDUCE": "1"},
-                  {"GANET_TMA_REDUCE": "0"}):
+    no_h = {"GANET_NO_HSCAN": "1"}
+    knob_sets = [{}, no_h, dict(no_h, GANET_NO_DIRECT="1"), {"GANET_NO_TMA": "1"},
+                 dict(no_h, GANET_TMA_REDUCE="1"), dict(no_h, GANET_TMA_REDUCE="0")]
+    fwd, grad, files = [], [], []
+    for i, knobs in enumerate(knob_sets):
         env = dict(os.environ)
-        for k in ("GANET_NO_TMA", "GANET_NO_DIRECT", "GANET_FORCE_DIRECT", "GANET_TMA_REDUCE"):
+        for k in ("GANET_NO_TMA", "GANET_NO_DIRECT", "GANET_FORCE_DIRECT", "GANET_TMA_REDUCE", "GANET_NO_HSCAN"):
             env.pop(k, None)
         env.update(knobs)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        f = str(tmp_path / ("grads%d.npz" % i))
+        r = subprocess.run([sys.executable, "-c", code, f], env=env, capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr[-2000:]
-        digests.append(r.stdout.strip().splitlines()[-1])
-    assert len(set(digests)) == 1, digests
+        a, b = r.stdout.strip().splitlines()[-1].split()
+        fwd.append(a); grad.append(b); files.append(f)
+    assert len(set(fwd)) == 1, fwd
+    assert len(set(grad[1:])) == 1, grad
+    new, old = np.load(files[0]), np.load(files[1])
+    for k in new.files:
+        assert_close(new[k], old[k], RTOL, "standard-layout vs transposed path: " + k)
 
 
 def test_lga_tiled_and_per_pixel_kernels_agree_bitwise(ops):
