@@ -748,7 +748,7 @@ static int launch_hscan_bwd(const float *x, const float *g, const float *a, cons
     if (!make_plane_map(&maps.go, go, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
     if (!make_plane_map(&maps.a, a, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
     if (!make_plane_map(&maps.gi, gi, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
-    if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, BW, D, 1, CU_TENSOR_MAP_SWIZZLE_32B)) return kNotApplicable;
+    if (!make_plane_map(&maps.mask, mask, 1, n_slices * D, H, W, BW, D, 1)) return kNotApplicable;
     if (!make_plane_map(&maps.g, g, 4, n_slices * 5, H, W, BW, 5, 1)) return kNotApplicable;
     const long long blocks = n_slices * H;
     if (blocks <= 0) return GANET_OK;

@@ -321,7 +321,7 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                     vx = *reinterpret_cast<const float4 *>(p + pl.off_x + o);
                     vg = *reinterpret_cast<const float4 *>(p + pl.off_go + o);
                     va = *reinterpret_cast<const float4 *>(p + pl.off_a + o);
-                    mw = *reinterpret_cast<const unsigned *>(p + pl.off_m + swz32((unsigned)((d0 + i) * BW + 4 * qi)));
+                    mw = *reinterpret_cast<const unsigned *>(p + pl.off_m + (unsigned)((d0 + i) * BW + 4 * qi));
                 }
                 xq[i][0] = vx.x; xq[i][1] = vx.y; xq[i][2] = vx.z; xq[i][3] = vx.w;
                 aq[i][0] = va.x; aq[i][1] = va.y; aq[i][2] = va.z; aq[i][3] = va.w;

@@ -89,6 +89,12 @@ int main(int argc, char **argv)
         {1, 32, 1, 8, 0, 1, "vertical strip, 128B rows, 8 stages"},
         {1, 32, 1, 2, 0, 1, "vertical strip, 128B rows, 2 stages (3 CTAs/SM)"},
         {1, 16, 1, 8, 0, 1, "vertical strip, 64B rows"},
+        {1, 64, 1, 4, 0, 1, "vertical strip, 256B rows, 4 stages"},
+        {1, 128, 1, 2, 0, 1, "vertical strip, 512B rows, 2 stages"},
+        {1, 128, 1, 1, 0, 1, "vertical strip, 512B rows, 1 stage (2 CTAs/SM)"},
+        {1, 32, 2, 4, 0, 1, "vertical strip, 128B rows, 2 rows per box, 4 stages"},
+        {1, 32, 4, 2, 0, 1, "vertical strip, 128B rows, 4 rows per box, 2 stages"},
+        {1, 16, 1, 16, 0, 1, "vertical strip, 64B rows, 16 stages"},
         {0, 4, 32, 2, 0, 1, "band 32 rows, 16B inner"},
         {0, 8, 16, 2, 0, 1, "band 16 rows, 32B inner"},
         {0, 8, 16, 2, 1, 1, "band 16 rows, 32B inner, swizzle32"},
