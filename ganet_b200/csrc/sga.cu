@@ -688,6 +688,16 @@ static bool hscan_ok(int D, int H, int W)
 
 constexpr int kHscanCtaBudget = 110 * 1024;       // two CTAs per SM
 
+// tuning aids: cap the stage rings of the horizontal kernels (fewer stages = more CTAs per SM)
+static int hscan_stage_cap(bool backward, int dflt)
+{
+    static int vf = -1, vb = -1;
+    if (vf < 0) { const char *e = getenv("GANET_HSCAN_STAGES"); vf = e ? atoi(e) : 0; }
+    if (vb < 0) { const char *e = getenv("GANET_HSCAN_BWD_STAGES"); vb = e ? atoi(e) : 0; }
+    const int v = backward ? vb : vf;
+    return v >= 1 ? v : dflt;
+}
+
 template <int DIR>
 static int launch_hscan_fwd(const float *x, const float *g, float *out, int D, int H, int W,
                             long long n_slices, cudaStream_t st)
@@ -698,7 +708,7 @@ static int launch_hscan_fwd(const float *x, const float *g, float *out, int D, i
     const int stage = hfwd_stage_bytes(D, BW);
     const int nb = (W + BW - 1) / BW;
     int S = (kHscanCtaBudget - 2048) / stage;
-    if (S > 8) S = 8;
+    if (S > hscan_stage_cap(false, 4)) S = hscan_stage_cap(false, 4);
     if (S > nb) S = nb;
     if (S < 2 && nb >= 2) return kNotApplicable;
     if (S < 1) S = 1;
@@ -737,7 +747,7 @@ static int launch_hscan_bwd(const float *x, const float *g, const float *a, cons
     const HBwdPlan pl = hbwd_plan(D, BW);
     const int nb = (W + BW - 1) / BW;
     int S = (kHscanCtaBudget - 2048) / pl.stage_bytes;
-    if (S > 4) S = 4;
+    if (S > hscan_stage_cap(true, 4)) S = hscan_stage_cap(true, 4);
     if (S > nb) S = nb;
     if (S < 2 && nb >= 2) return kNotApplicable;
     if (S < 1) S = 1;

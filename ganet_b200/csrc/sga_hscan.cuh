@@ -276,28 +276,32 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
     }
 
     // ---------------- consumer warp: lane = depth chunk
+    //
+    // A single warp walks the line, and a warp issues in order: every shuffle reduction that sits
+    // between two scan steps is paid in full (the first version of this kernel reduced five sums and an
+    // arg-max per step, ~720 cycles per step: 3.2 TB/s).  So a quad of four steps is processed in
+    // three phases, and only phase 1 is sequential:
+    //   0  what does not depend on T, for the four steps side by side (their shuffles pipeline):
+    //      arg-max of the aggregate, sum over depth of the mask-selected gradOut
+    //   1  the recurrence T[t+1] -> T[t]; the sum over depth of T, which the max-path term needs,
+    //      follows from the recurrence itself:
+    //          sum_d T[d,t] = sum_d T0[d,t] + (w1+w2+w3+w4)(t+1) * sum_d T[d,t+1]
+    //                         - w2(t+1) * T[0,t+1] - w3(t+1) * T[D-1,t+1]
+    //      (two broadcasts instead of a five-level reduction on the critical path)
+    //   2  the guidance-gradient dot products of the four steps side by side, one packed
+    //      four-value warp sum each; gradInput
     const int d0 = K * lane;
     const long long HW = (long long)H * W;
     float *ggrow = gg + s * 5 * HW + (long long)h * W;    // + k * HW + column
     int32_t *mirow = max_idx ? max_idx + s * HW + (long long)h * W : nullptr;
-
-    // first arg-max over depth of a row held as K values per lane (strict >: first maximum)
-    auto row_argmax = [&](const float (&r)[K], float &vmax) -> int {
-        float best = (FULL || d0 < D) ? r[0] : -INFINITY;
-        int bi = d0;
-#pragma unroll
-        for (int i = 1; i < K; i++)
-            if ((FULL || d0 + i < D) && r[i] > best) { best = r[i]; bi = d0 + i; }
-        vmax = group_max<32>(best);
-        return __reduce_min_sync(kFullMask, best == vmax ? bi : 0x7fffffff);
-    };
+    const int lane_last = (D - 1) / K, i_last = (D - 1) - K * lane_last;      // owner of depth D-1
 
     float Tn[K], xn[K], wn[5];                            // T, x and guidance of position t+1
 #pragma unroll
     for (int i = 0; i < K; i++) { Tn[i] = 0.f; xn[i] = 0.f; }
 #pragma unroll
     for (int k = 0; k < 5; k++) wn[k] = 0.f;
-    float sum_tn = 0.f;
+    float sum_tn = 0.f;                                   // sum over depth of Tn
     bool has_next = false;
     int col_next = 0;                                     // column of position t+1
     int slot = 0, phase = 0;
@@ -336,81 +340,145 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                 const float4 v = *reinterpret_cast<const float4 *>(gt + k * BW + 4 * qi);
                 gq[k][0] = v.x; gq[k][1] = v.y; gq[k][2] = v.z; gq[k][3] = v.w;
             }
+
+            // ---- phase 0: per step, independent of T -------------------------------------
+            float amax[4], st0[4];
+            int idx[4];
+            {
+                float best[4];
+                int bi[4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) {
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+                    float bv = (FULL || d0 < D) ? aq[0][e] : -INFINITY;       // strict >: first maximum
+                    int bd = d0;
+                    float t0s = tq[0][e];
+#pragma unroll
+                    for (int i = 1; i < K; i++) {
+                        if ((FULL || d0 + i < D) && aq[i][e] > bv) { bv = aq[i][e]; bd = d0 + i; }
+                        t0s += tq[i][e];
+                    }
+                    best[ss] = bv; bi[ss] = bd; st0[ss] = t0s;
+                }
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) amax[ss] = group_max<32>(best[ss]);
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++)
+                    idx[ss] = __reduce_min_sync(kFullMask, best[ss] == amax[ss] ? bi[ss] : 0x7fffffff);
+                const float v = warp_sum4(st0[0], st0[1], st0[2], st0[3], lane);
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) st0[ss] = __shfl_sync(kFullMask, v, 8 * ss);
+            }
+
+            // ---- phase 1: the recurrence (t0 -> T in place in tq) -----------------------------
+            float Tin[K], xin[K], sv[4];
+            const float sum_in = sum_tn;
+            const bool has_in = has_next;
+            const int col_in = col_next;
+#pragma unroll
+            for (int i = 0; i < K; i++) { Tin[i] = Tn[i]; xin[i] = xn[i]; }
 #pragma unroll
             for (int ss = 0; ss < 4; ss++) {
-                const int e = (DIR == 0) ? 3 - ss : ss;   // compile-time after unrolling
-                const int col = c0 + 4 * qi + e;
-                float xv[K], av[K], w[5], tc[K];
-#pragma unroll
-                for (int i = 0; i < K; i++) { xv[i] = xq[i][e]; av[i] = aq[i][e]; }
-#pragma unroll
-                for (int k = 0; k < 5; k++) w[k] = gq[k][e];
-
-                // arg-max of the aggregate at THIS position: the max-path target of the step
-                // t+1 -> t, and max_idx
-                float amax;
-                const int idx_t = row_argmax(av, amax);
-                if (mirow && lane == 0) mirow[col] = idx_t;
-
-                float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                if (has_next) {
-                    // guidance gradients 1..4 of position t+1 need A at position t (:210-281)
-                    const float aup = __shfl_up_sync(kFullMask, av[K - 1], 1);    // A[d0-1, t]
-                    const float adn = __shfl_down_sync(kFullMask, av[0], 1);      // A[d0+K, t]
+                const int e = (DIR == 0) ? 3 - ss : ss;
+                float scur = st0[ss];
+                if (ss > 0 || has_in) {
                     const float up = __shfl_up_sync(kFullMask, Tn[K - 1], 1);     // T[d0-1, t+1]
                     const float dn = __shfl_down_sync(kFullMask, Tn[0], 1);       // T[d0+K, t+1]
+                    float tl = Tn[K - 1];
+                    if (!FULL) {
+#pragma unroll
+                        for (int i = 0; i < K; i++)
+                            if (i == i_last) tl = Tn[i];
+                    }
+                    const float t_first = __shfl_sync(kFullMask, Tn[0], 0);       // T[0, t+1]
+                    const float t_last = __shfl_sync(kFullMask, tl, FULL ? 31 : lane_last);   // T[D-1, t+1]
                     const float inj = sum_tn * wn[4];                             // max-path term (:167-178)
 #pragma unroll
                     for (int i = 0; i < K; i++) {
                         const int d = d0 + i;
-                        const float am = (i == 0) ? aup : av[i == 0 ? 0 : i - 1];
-                        const float apn = (i == K - 1) ? adn : av[i == K - 1 ? K - 1 : i + 1];
-                        s1 += Tn[i] * av[i];
-                        s2 += Tn[i] * ((d >= 1) ? am : xn[i]);
-                        s3 += Tn[i] * ((d + 1 < D) ? apn : xn[i]);
                         const float tm = (i == 0) ? up : Tn[i == 0 ? 0 : i - 1];
                         const float tp = (i == K - 1) ? dn : Tn[i == K - 1 ? K - 1 : i + 1];
                         float v = tq[i][e];
                         v += Tn[i] * wn[1];
                         if (d + 1 < D) v += tp * wn[2];
                         if (d >= 1) v += tm * wn[3];
-                        if (d == idx_t) v += inj;
-                        tc[i] = (FULL || d < D) ? v : 0.f;
+                        if (d == idx[ss]) v += inj;
+                        tq[i][e] = (FULL || d < D) ? v : 0.f;
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < K; i++) tc[i] = tq[i][e];
+                    scur += sum_tn * (wn[1] + wn[2] + wn[3] + wn[4]) - wn[2] * t_first - wn[3] * t_last;
                 }
+                sv[ss] = scur;
+                sum_tn = scur;
+#pragma unroll
+                for (int i = 0; i < K; i++) Tn[i] = tq[i][e];
+#pragma unroll
+                for (int k = 0; k < 5; k++) wn[k] = gq[k][e];
+            }
 
+            // ---- phase 2: guidance gradients of the four steps, then gradInput ----------------
+            {
+                float s0[4], s1[4], s2[4], s3[4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) {
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+                    const int ep = (DIR == 0) ? e + 1 : e - 1;     // the step processed before (position t+1)
+                    s0[ss] = 0.f; s1[ss] = 0.f; s2[ss] = 0.f; s3[ss] = 0.f;
+                    // A[d0-1, t] and A[d0+K, t]
+                    const float aup = __shfl_up_sync(kFullMask, aq[K - 1][e], 1);
+                    const float adn = __shfl_down_sync(kFullMask, aq[0][e], 1);
+#pragma unroll
+                    for (int i = 0; i < K; i++) {
+                        const int d = d0 + i;
+                        const float tp_ = (ss == 0) ? Tin[i] : tq[i][ss == 0 ? e : ep];      // T[d, t+1]
+                        const float xp_ = (ss == 0) ? xin[i] : xq[i][ss == 0 ? e : ep];      // x[d, t+1]
+                        const float am = (i == 0) ? aup : aq[i == 0 ? 0 : i - 1][e];
+                        const float apn = (i == K - 1) ? adn : aq[i == K - 1 ? K - 1 : i + 1][e];
+                        s0[ss] += tq[i][e] * xq[i][e];
+                        s1[ss] += tp_ * aq[i][e];
+                        s2[ss] += tp_ * ((d >= 1) ? am : xp_);
+                        s3[ss] += tp_ * ((d + 1 < D) ? apn : xp_);
+                    }
+                }
+                float tot[4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) tot[ss] = warp_sum4(s0[ss], s1[ss], s2[ss], s3[ss], lane);
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) {
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+                    const int col = c0 + 4 * qi + e;
+                    const int colp = (ss == 0) ? col_in : ((DIR == 0) ? col + 1 : col - 1);
+                    const bool hasp = (ss > 0) || has_in;
+                    const float sp = (ss == 0) ? sum_in : sv[ss == 0 ? 0 : ss - 1];
+                    // lanes 0 / 8 / 16 / 24 hold the sums s0 (position t) / s1 / s2 / s3 (position t+1)
+                    if ((lane & 7) == 0) {
+                        const int k = lane >> 3;
+                        if (k == 0) ggrow[col] = tot[ss];
+                        else if (hasp) ggrow[k * HW + colp] = tot[ss];
+                    }
+                    if (lane == 1 && hasp) ggrow[4 * HW + colp] = sp * amax[ss];
+                    if (mirow && lane == 2) mirow[col] = idx[ss];
+                }
                 // gradInput (:164, :177, :200-207), in place over the gradOut tile
-                float s0 = 0.f, st = 0.f;
 #pragma unroll
-                for (int i = 0; i < K; i++) {
-                    const int d = d0 + i;
-                    float v = tc[i] * w[0];
-                    if (d == 0) v += tc[i] * w[2];
-                    if (d == D - 1) v += tc[i] * w[3];
-                    tq[i][e] = v;
-                    s0 += tc[i] * xv[i];
-                    st += tc[i];
+                for (int ss = 0; ss < 4; ss++) {
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+#pragma unroll
+                    for (int i = 0; i < K; i++) {
+                        const int d = d0 + i;
+                        const float t = tq[i][e];
+                        float v = t * gq[0][e];
+                        if (d == 0) v += t * gq[2][e];
+                        if (d == D - 1) v += t * gq[3][e];
+                        tq[i][e] = v;
+                    }
                 }
-                st = group_sum<32>(st);
-                const float tot = warp_sum4(s0, s1, s2, s3, lane);
-                // lanes 0 / 8 / 16 / 24 hold the sums s0 (position t) / s1 / s2 / s3 (position t+1)
-                if ((lane & 7) == 0) {
-                    const int k = lane >> 3;
-                    if (k == 0) ggrow[col] = tot;
-                    else if (has_next) ggrow[k * HW + col_next] = tot;
-                }
-                if (lane == 1 && has_next) ggrow[4 * HW + col_next] = sum_tn * amax;
-
+            }
+            {
+                const int e_last = (DIR == 0) ? 0 : 3;
 #pragma unroll
-                for (int i = 0; i < K; i++) { Tn[i] = tc[i]; xn[i] = xv[i]; }
-#pragma unroll
-                for (int k = 0; k < 5; k++) wn[k] = w[k];
-                sum_tn = st;
+                for (int i = 0; i < K; i++) xn[i] = xq[i][e_last];
                 has_next = true;
-                col_next = col;
+                col_next = c0 + 4 * qi + e_last;
             }
 #pragma unroll
             for (int i = 0; i < K; i++)

