@@ -519,6 +519,14 @@ static int stream_hint(long long n_slices, int D, int H, int W)
 // (test_tma_and_ldg_kernels_agree_bitwise); measured on B200 at 2x32x192x240x624: backward
 // 38.3-39.3 -> 36.1-36.2 ms with kept aggregates, 54.1 -> 51.1 ms without.  GANET_TMA_REDUCE=0
 // restores the load + add + store form.
+// L2 prefetch distance (rows beyond the shared-memory ring) of the vertical TMA kernels
+static int vert_prefetch()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GANET_VERT_PREFETCH"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 static bool tma_reduce_enabled()
 {
     static int v = -1;
@@ -570,7 +578,7 @@ static int launch_tma_fwd(VCfg c, const float *x, const float *g, float *out, ui
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
         k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, dir, ids, D, H, strips, S,    \
-                                                           stream_hint(n_slices, D, H, W));    \
+                                                           stream_hint(n_slices, D, H, W), vert_prefetch()); \
     } else
     GANET_VERT_CFGS(X) { return kNotApplicable; }
 #undef X
@@ -612,7 +620,7 @@ static int launch_tma_bwd(VCfg c, const float *x, const float *g, const float *a
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
         k<<<(unsigned)blocks, (c.NW + 1) * 32, smem, st>>>(maps, gi, gg, dir, mask_id,         \
                                                            acc_mode, D, H, W, strips, S,       \
-                                                           stream_hint(n_slices, D, H, W));    \
+                                                           stream_hint(n_slices, D, H, W), vert_prefetch()); \
     } else
     GANET_VERT_CFGS(X) { return kNotApplicable; }
 #undef X
@@ -667,6 +675,15 @@ static bool hscan_enabled()
     static int v = -1;
     if (v < 0) v = getenv("GANET_NO_HSCAN") ? 0 : 1;
     return v != 0 && tma_enabled();
+}
+
+// L2 prefetch distance (tiles beyond the shared-memory ring) of the horizontal kernels
+static int hscan_prefetch(bool backward)
+{
+    static int vf = -1, vb = -1;
+    if (vf < 0) { const char *e = getenv("GANET_HSCAN_PREFETCH"); vf = e ? atoi(e) : 4; }
+    if (vb < 0) { const char *e = getenv("GANET_HSCAN_BWD_PREFETCH"); vb = e ? atoi(e) : 4; }
+    return backward ? vb : vf;
 }
 
 static int hscan_k(int D)
@@ -728,7 +745,7 @@ static int launch_hscan_fwd(const float *x, const float *g, float *out, int D, i
         auto k = full ? kf : kp;                                                               \
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
-        k<<<(unsigned)blocks, 64, smem, st>>>(maps, D, H, W, S);                               \
+        k<<<(unsigned)blocks, 64, smem, st>>>(maps, D, H, W, S, hscan_prefetch(false));                               \
     } else
     GANET_HSCAN_KS(X) { return kNotApplicable; }
 #undef X
@@ -771,7 +788,7 @@ static int launch_hscan_bwd(const float *x, const float *g, const float *a, cons
         auto k = full ? kf : kp;                                                               \
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
             cudaSuccess) { cudaGetLastError(); return kNotApplicable; }                        \
-        k<<<(unsigned)blocks, 64, smem, st>>>(maps, gg, max_idx, mask_id, accumulate, D, H, W, S); \
+        k<<<(unsigned)blocks, 64, smem, st>>>(maps, gg, max_idx, mask_id, accumulate, D, H, W, S, hscan_prefetch(true)); \
     } else
     GANET_HSCAN_KS(X) { return kNotApplicable; }
 #undef X

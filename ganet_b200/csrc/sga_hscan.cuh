@@ -80,7 +80,7 @@ __device__ __forceinline__ unsigned char *align1k(unsigned char *p)
 // ---------------------------------------------------------------------------
 template <int K, int BW, int DIR, bool FULL>
 __global__ void __launch_bounds__(64)
-sga_hscan_fwd_kernel(const __grid_constant__ HFwdMaps maps, int D, int H, int W, int S)
+sga_hscan_fwd_kernel(const __grid_constant__ HFwdMaps maps, int D, int H, int W, int S, int PF)
 {
     static_assert(K % 2 == 0, "depth parity must be a compile-time property");
     static_assert(BW == 16 || BW == 32, "tile width");
@@ -114,9 +114,18 @@ sga_hscan_fwd_kernel(const __grid_constant__ HFwdMaps maps, int D, int H, int W,
                 tma_load_3d(p, &maps.x, &full[st], col_of(b), h, c2x);
                 tma_load_3d(p + xbytes, &maps.g, &full[st], col_of(b), h, c2g);
             };
+            // tiles S .. S+PF-1 ahead of the ring are pulled into L2 (PF = 0: off)
+            auto prefetch = [&](int b) {
+                if (b < nb) {
+                    tma_prefetch_3d(&maps.x, col_of(b), h, c2x);
+                    tma_prefetch_3d(&maps.g, col_of(b), h, c2g);
+                }
+            };
             for (int b = 0; b < S && b < nb; b++) issue(b);
+            for (int b = S; b < S + PF; b++) prefetch(b);
             for (int b = 0; b < nb; b++) {
                 const int st = b % S;
+                if (PF > 0) prefetch(b + S + PF);
                 mbar_wait(&done[st], (b / S) & 1);
                 tma_store_3d(&maps.out, smem + (size_t)st * stage_bytes, col_of(b), h, c2x);
                 tma_commit();
@@ -222,7 +231,7 @@ template <int K, int BW, int DIR, bool FULL>
 __global__ void __launch_bounds__(64)
 sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ gg,
                      int32_t *__restrict__ max_idx, int mask_id, int accumulate, int D, int H, int W,
-                     int S)
+                     int S, int PF)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = align1k(smem_raw);
@@ -257,9 +266,20 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                 tma_load_3d(p + pl.off_m, &maps.mask, &full[st], col_of(b), h, c2x);
                 tma_load_3d(p + pl.off_g, &maps.g, &full[st], col_of(b), h, c2g);
             };
+            auto prefetch = [&](int b) {
+                if (b < nb) {
+                    tma_prefetch_3d(&maps.x, col_of(b), h, c2x);
+                    tma_prefetch_3d(&maps.go, col_of(b), h, c2x);
+                    tma_prefetch_3d(&maps.a, col_of(b), h, c2x);
+                    tma_prefetch_3d(&maps.mask, col_of(b), h, c2x);
+                    tma_prefetch_3d(&maps.g, col_of(b), h, c2g);
+                }
+            };
             for (int b = 0; b < S && b < nb; b++) issue(b);
+            for (int b = S; b < S + PF; b++) prefetch(b);
             for (int b = 0; b < nb; b++) {
                 const int st = b % S;
+                if (PF > 0) prefetch(b + S + PF);
                 mbar_wait(&done[st], (b / S) & 1);
                 unsigned char *p = smem + (size_t)st * pl.stage_bytes;
                 if (accumulate) tma_reduce_add_3d(&maps.gi, p + pl.off_go, col_of(b), h, c2x);

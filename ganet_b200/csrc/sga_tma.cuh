@@ -69,7 +69,7 @@ __host__ __device__ inline BwdPlan bwd_plan(int D)
 template <int K, int MAXW, int MODE, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32 + 32)
 sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids, int D, int H,
-                   int strips, int S, int stream_hint)
+                   int strips, int S, int stream_hint, int PF)
 {
     static_assert(K % 2 == 0, "depth parity must be a compile-time property");
     constexpr bool kThree = (MODE == VMODE_FIRST3);       // merge down with the two horizontal aggregates
@@ -122,9 +122,21 @@ sga_tma_fwd_kernel(const __grid_constant__ TmaFwdMaps maps, int dir, MaskIds ids
                 }
                 if (MODE == VMODE_COMBINE) tma_load_3d(b + pl.off_m, &maps.mask, &full[st], w0, h, c2x);
             };
+            // rows beyond the ring are pulled into L2 (PF rows ahead; 0 = off)
+            auto prefetch = [&](int t) {
+                if (t < H) {
+                    const int h = (dir == 0) ? t : H - 1 - t;
+                    tma_prefetch_3d(&maps.x, w0, h, c2x);
+                    if (kThree) { tma_prefetch_3d(&maps.a2, w0, h, c2x); tma_prefetch_3d(&maps.a3, w0, h, c2x); }
+                    else if (kCombine) tma_prefetch_3d(&maps.out, w0, h, c2x);
+                    if (MODE == VMODE_COMBINE) tma_prefetch_3d(&maps.mask, w0, h, c2x);
+                }
+            };
             for (int t = 0; t < S && t < H; t++) issue(t);
+            for (int t = S; t < S + PF; t++) prefetch(t);
             for (int t = 0; t < H; t++) {
                 const int st = t % S;
+                if (PF > 0) prefetch(t + S + PF);
                 mbar_wait(&done[st], (t / S) & 1);
                 const int h = (dir == 0) ? t : H - 1 - t;
                 unsigned char *b = smem + (size_t)st * pl.stage_bytes;
@@ -367,7 +379,7 @@ template <int K, int MAXW, bool FULL>
 __global__ void __launch_bounds__(MAXW * 32 + 32)
 sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old, float *__restrict__ gg,
                    int dir, int mask_id, int accumulate, int D, int H, int W, int strips, int S,
-                   int stream_hint)
+                   int stream_hint, int PF)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
@@ -415,9 +427,20 @@ sga_tma_bwd_kernel(const __grid_constant__ TmaBwdMaps maps, const float *gi_old,
                 tma_load_3d(b + pl.off_g, &maps.g, &full[st], w0, row_of(t), c2g);
                 if (t >= 1) tma_load_3d(b + pl.off_a, &maps.a, &full[st], w0, row_of(t - 1), c2x);
             };
+            auto prefetch = [&](int it) {
+                if (it < H) {
+                    const int t = H - 1 - it;
+                    tma_prefetch_3d(&maps.x, w0, row_of(t), c2x);
+                    tma_prefetch_3d(&maps.go, w0, row_of(t), c2x);
+                    tma_prefetch_3d(&maps.mask, w0, row_of(t), c2x);
+                    if (t >= 1) tma_prefetch_3d(&maps.a, w0, row_of(t - 1), c2x);
+                }
+            };
             for (int it = 0; it < S && it < H; it++) issue(it);
+            for (int it = S; it < S + PF; it++) prefetch(it);
             for (int it = 0; it < H; it++) {
                 const int st = it % S;
+                if (PF > 0) prefetch(it + S + PF);
                 mbar_wait(&done[st], (it / S) & 1);
                 unsigned char *b = smem + (size_t)st * pl.stage_bytes;
                 if (accumulate == 2) tma_reduce_add_3d(&maps.gi, b + pl.off_go, w0, row_of(H - 1 - it), c2x);

@@ -70,6 +70,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// Pull a box into L2 only (no shared memory, no barrier): lets the producer keep many more bytes
+// in flight towards DRAM than the shared-memory ring can hold; the later tma_load_3d hits L2.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1,
                                              int c2)
 {
