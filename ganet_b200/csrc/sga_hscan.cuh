@@ -222,17 +222,35 @@ __device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, i
 
 // ---------------------------------------------------------------------------
 // backward (reverse sweep) of one horizontal direction.  DIR 0 = right (walks the columns
-// DEscending), 1 = left (ascending).  gradInput leaves through the gradOut tile (in place):
-// plain TMA store, or TMA reduce-add when `accumulate`.  The five guidance gradients of a pixel
-// are written straight to global memory by five lanes (80/D bytes per voxel).
-// max_idx (optional): depth arg-max of the aggregate at every pixel (MaxDepth, :50-64).
+// DEscending), 1 = left (ascending).  One CTA = one image row; THREE warps:
+//
+//   warp 1  producer: TMA tiles (32 columns, 1 row, D planes) of x, gradOut, A, mask, guidance into a
+//           ring of S stages; stores the gradOut tile, which by then holds gradInput (plain store, or
+//           reduce-add when `accumulate`)
+//   warp 0  "T warp": the sequential part.  Per quad of four scan steps: mask-select gradOut -> T0,
+//           depth arg-max of the aggregate (max-path target, max_idx), then the recurrence
+//           T[t+1] -> T[t]; the sum over depth of T that the max-path term needs follows from the
+//           recurrence itself,
+//               sum_d T[d,t] = sum_d T0[d,t] + (w1+w2+w3+w4)(t+1) * sum_d T[d,t+1]
+//                              - w2(t+1) * T[0,t+1] - w3(t+1) * T[D-1,t+1],
+//           so only two broadcasts sit on the critical path.  T is written over the gradOut tile.
+//   warp 2  "gradient warp", one quad behind (one named barrier per quad): reads T, x, A; the five
+//           guidance-gradient dot products of four steps side by side (one packed four-value warp
+//           sum each, written straight to global memory: 80/D bytes per voxel), then
+//           gradInput = T * w0 (+ boundary terms) over the T values in place.
+//
+// Why this shape (profiles/r02_*): a row tile of 64-byte rows moves half the bytes per TMA request
+// of the 128-byte rows and ran request-bound at 3.2 TB/s; 128-byte rows cost 80 KB per stage, i.e.
+// two stages and ONE row per SM, and a single warp per row issues ~250 instructions per step in order --
+// too slow for one SM.  Splitting the step between two warps halves that.
 // ---------------------------------------------------------------------------
 template <int K, int BW, int DIR, bool FULL>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(96)
 sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ gg,
                      int32_t *__restrict__ max_idx, int mask_id, int accumulate, int D, int H, int W,
                      int S, int PF)
 {
+    static_assert(BW == 32, "128-byte rows");
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = align1k(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,6 +259,7 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
     const HBwdPlan pl = hbwd_plan(D, BW);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * pl.stage_bytes);
     uint64_t *done = full + S;
+    float *svbuf = reinterpret_cast<float *>(done + S);   // [2][4]: sum over depth of T, per quad parity
     const int c2x = (int)(s * D), c2g = (int)(s * 5);
     const int nb = (W + BW - 1) / BW;
 
@@ -260,11 +279,11 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                 const int st = b % S;
                 unsigned char *p = smem + (size_t)st * pl.stage_bytes;
                 mbar_arrive_expect_tx(&full[st], tx);
-                tma_load_3d(p + pl.off_x, &maps.x, &full[st], col_of(b), h, c2x);
                 tma_load_3d(p + pl.off_go, &maps.go, &full[st], col_of(b), h, c2x);
-                tma_load_3d(p + pl.off_a, &maps.a, &full[st], col_of(b), h, c2x);
                 tma_load_3d(p + pl.off_m, &maps.mask, &full[st], col_of(b), h, c2x);
+                tma_load_3d(p + pl.off_a, &maps.a, &full[st], col_of(b), h, c2x);
                 tma_load_3d(p + pl.off_g, &maps.g, &full[st], col_of(b), h, c2g);
+                tma_load_3d(p + pl.off_x, &maps.x, &full[st], col_of(b), h, c2x);
             };
             auto prefetch = [&](int b) {
                 if (b < nb) {
@@ -272,7 +291,6 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                     tma_prefetch_3d(&maps.go, col_of(b), h, c2x);
                     tma_prefetch_3d(&maps.a, col_of(b), h, c2x);
                     tma_prefetch_3d(&maps.mask, col_of(b), h, c2x);
-                    tma_prefetch_3d(&maps.g, col_of(b), h, c2g);
                 }
             };
             for (int b = 0; b < S && b < nb; b++) issue(b);
@@ -295,36 +313,163 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
         return;
     }
 
-    // ---------------- consumer warp: lane = depth chunk
-    //
-    // A single warp walks the line, and a warp issues in order: every shuffle reduction that sits
-    // between two scan steps is paid in full (the first version of this kernel reduced five sums and an
-    // arg-max per step, ~720 cycles per step: 3.2 TB/s).  So a quad of four steps is processed in
-    // three phases, and only phase 1 is sequential:
-    //   0  what does not depend on T, for the four steps side by side (their shuffles pipeline):
-    //      arg-max of the aggregate, sum over depth of the mask-selected gradOut
-    //   1  the recurrence T[t+1] -> T[t]; the sum over depth of T, which the max-path term needs,
-    //      follows from the recurrence itself:
-    //          sum_d T[d,t] = sum_d T0[d,t] + (w1+w2+w3+w4)(t+1) * sum_d T[d,t+1]
-    //                         - w2(t+1) * T[0,t+1] - w3(t+1) * T[D-1,t+1]
-    //      (two broadcasts instead of a five-level reduction on the critical path)
-    //   2  the guidance-gradient dot products of the four steps side by side, one packed
-    //      four-value warp sum each; gradInput
     const int d0 = K * lane;
     const long long HW = (long long)H * W;
-    float *ggrow = gg + s * 5 * HW + (long long)h * W;    // + k * HW + column
-    int32_t *mirow = max_idx ? max_idx + s * HW + (long long)h * W : nullptr;
-    const int lane_last = (D - 1) / K, i_last = (D - 1) - K * lane_last;      // owner of depth D-1
-
-    float Tn[K], xn[K], wn[5];                            // T, x and guidance of position t+1
-#pragma unroll
-    for (int i = 0; i < K; i++) { Tn[i] = 0.f; xn[i] = 0.f; }
-#pragma unroll
-    for (int k = 0; k < 5; k++) wn[k] = 0.f;
-    float sum_tn = 0.f;                                   // sum over depth of Tn
-    bool has_next = false;
-    int col_next = 0;                                     // column of position t+1
     int slot = 0, phase = 0;
+    int quad_parity = 0;
+
+    if (warp == 0) {
+        // ---------------- T warp: lane = depth chunk
+        int32_t *mirow = max_idx ? max_idx + s * HW + (long long)h * W : nullptr;
+        const int lane_last = (D - 1) / K, i_last = (D - 1) - K * lane_last;      // owner of depth D-1
+        float Tn[K], wn[5];                               // T and guidance of position t+1
+#pragma unroll
+        for (int i = 0; i < K; i++) Tn[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; k++) wn[k] = 0.f;
+        float sum_tn = 0.f;                               // sum over depth of Tn
+        bool has_next = false;
+
+        for (int b = 0; b < nb; b++) {
+            unsigned char *p = smem + (size_t)slot * pl.stage_bytes;
+            const int c0 = BW * (DIR == 0 ? nb - 1 - b : b);
+            mbar_wait(&full[slot], phase);
+            const float *gt = reinterpret_cast<const float *>(p + pl.off_g);
+            uint4 mq[K];                                  // mask bytes of 16 columns (four quads)
+#pragma unroll 1
+            for (int qq = 0; qq < BW / 4; qq++) {
+                const int qi = (DIR == 0) ? BW / 4 - 1 - qq : qq;
+                if (c0 + 4 * qi >= W) continue;           // columns past the image (both warps skip them)
+                if ((DIR == 0) ? (qi & 3) == 3 : (qi & 3) == 0) {     // a new group of 16 columns (W % 16 == 0)
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                        mq[i] = (FULL || d0 + i < D)
+                                    ? *reinterpret_cast<const uint4 *>(p + pl.off_m + (unsigned)((d0 + i) * BW + 16 * (qi >> 2)))
+                                    : make_uint4(~0u, ~0u, ~0u, ~0u);
+                }
+                float tq[K][4], aq[K][4], gq[5][4];
+                const int wsel = qi & 3;
+#pragma unroll
+                for (int i = 0; i < K; i++) {
+                    float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), va = vg;
+                    if (FULL || d0 + i < D) {
+                        const unsigned o = tile_swz<BW>((unsigned)(((d0 + i) * BW + 4 * qi) * 4));
+                        vg = *reinterpret_cast<const float4 *>(p + pl.off_go + o);
+                        va = *reinterpret_cast<const float4 *>(p + pl.off_a + o);
+                    }
+                    const unsigned mw = wsel == 0 ? mq[i].x : wsel == 1 ? mq[i].y : wsel == 2 ? mq[i].z : mq[i].w;
+                    aq[i][0] = va.x; aq[i][1] = va.y; aq[i][2] = va.z; aq[i][3] = va.w;
+                    // get_temp_grad (:38-48): gradOut where this direction won the max
+                    tq[i][0] = ((mw & 0xffu) == (unsigned)mask_id) ? vg.x : 0.f;
+                    tq[i][1] = (((mw >> 8) & 0xffu) == (unsigned)mask_id) ? vg.y : 0.f;
+                    tq[i][2] = (((mw >> 16) & 0xffu) == (unsigned)mask_id) ? vg.z : 0.f;
+                    tq[i][3] = ((mw >> 24) == (unsigned)mask_id) ? vg.w : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(gt + k * BW + 4 * qi);
+                    gq[k][0] = v.x; gq[k][1] = v.y; gq[k][2] = v.z; gq[k][3] = v.w;
+                }
+
+                // ---- per step, independent of T: arg-max of the aggregate, sum of T0 ----------
+                float st0[4];
+                int idx[4];
+                {
+                    float best[4], amax[4];
+                    int bi[4];
+#pragma unroll
+                    for (int ss = 0; ss < 4; ss++) {
+                        const int e = (DIR == 0) ? 3 - ss : ss;
+                        float bv = (FULL || d0 < D) ? aq[0][e] : -INFINITY;   // strict >: first maximum
+                        int bd = d0;
+                        float t0s = tq[0][e];
+#pragma unroll
+                        for (int i = 1; i < K; i++) {
+                            if ((FULL || d0 + i < D) && aq[i][e] > bv) { bv = aq[i][e]; bd = d0 + i; }
+                            t0s += tq[i][e];
+                        }
+                        best[ss] = bv; bi[ss] = bd; st0[ss] = t0s;
+                    }
+#pragma unroll
+                    for (int ss = 0; ss < 4; ss++) amax[ss] = group_max<32>(best[ss]);
+#pragma unroll
+                    for (int ss = 0; ss < 4; ss++)
+                        idx[ss] = __reduce_min_sync(kFullMask, best[ss] == amax[ss] ? bi[ss] : 0x7fffffff);
+                    const float v = warp_sum4(st0[0], st0[1], st0[2], st0[3], lane);
+#pragma unroll
+                    for (int ss = 0; ss < 4; ss++) st0[ss] = __shfl_sync(kFullMask, v, 8 * ss);
+                }
+                if (mirow && lane < 4) {
+                    const int ss = lane;
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+                    mirow[c0 + 4 * qi + e] = ss == 0 ? idx[0] : ss == 1 ? idx[1] : ss == 2 ? idx[2] : idx[3];
+                }
+
+                // ---- the recurrence (t0 -> T in place in tq) -----------------------------------
+                float sv[4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ss++) {
+                    const int e = (DIR == 0) ? 3 - ss : ss;
+                    float scur = st0[ss];
+                    if (ss > 0 || has_next) {
+                        const float up = __shfl_up_sync(kFullMask, Tn[K - 1], 1);     // T[d0-1, t+1]
+                        const float dn = __shfl_down_sync(kFullMask, Tn[0], 1);       // T[d0+K, t+1]
+                        float tl = Tn[K - 1];
+                        if (!FULL) {
+#pragma unroll
+                            for (int i = 0; i < K; i++)
+                                if (i == i_last) tl = Tn[i];
+                        }
+                        const float t_first = __shfl_sync(kFullMask, Tn[0], 0);       // T[0, t+1]
+                        const float t_last = __shfl_sync(kFullMask, tl, FULL ? 31 : lane_last);   // T[D-1, t+1]
+                        const float inj = sum_tn * wn[4];                             // max-path term (:167-178)
+#pragma unroll
+                        for (int i = 0; i < K; i++) {
+                            const int d = d0 + i;
+                            const float tm = (i == 0) ? up : Tn[i == 0 ? 0 : i - 1];
+                            const float tp = (i == K - 1) ? dn : Tn[i == K - 1 ? K - 1 : i + 1];
+                            float v = tq[i][e];
+                            v += Tn[i] * wn[1];
+                            if (d + 1 < D) v += tp * wn[2];
+                            if (d >= 1) v += tm * wn[3];
+                            if (d == idx[ss]) v += inj;
+                            tq[i][e] = (FULL || d < D) ? v : 0.f;
+                        }
+                        scur += sum_tn * (wn[1] + wn[2] + wn[3] + wn[4]) - wn[2] * t_first - wn[3] * t_last;
+                    }
+                    sv[ss] = scur;
+                    sum_tn = scur;
+#pragma unroll
+                    for (int i = 0; i < K; i++) Tn[i] = tq[i][e];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) wn[k] = gq[k][e];
+                }
+                has_next = true;
+
+                // T over the gradOut tile, the four sums beside it; the gradient warp takes over
+#pragma unroll
+                for (int i = 0; i < K; i++)
+                    if (FULL || d0 + i < D)
+                        *reinterpret_cast<float4 *>(p + pl.off_go + tile_swz<BW>((unsigned)(((d0 + i) * BW + 4 * qi) * 4))) =
+                            make_float4(tq[i][0], tq[i][1], tq[i][2], tq[i][3]);
+                if (lane == 0)
+                    *reinterpret_cast<float4 *>(svbuf + 4 * quad_parity) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                quad_parity ^= 1;
+                named_barrier(1, 64);
+            }
+            if (++slot == S) { slot = 0; phase ^= 1; }
+        }
+        return;
+    }
+
+    // ---------------- gradient warp: lane = depth chunk, one quad behind the T warp
+    float *ggrow = gg + s * 5 * HW + (long long)h * W;    // + k * HW + column
+    float Tin[K], xin[K];                                 // T and x of position t+1
+#pragma unroll
+    for (int i = 0; i < K; i++) { Tin[i] = 0.f; xin[i] = 0.f; }
+    float sum_in = 0.f;
+    bool has_in = false;
+    int col_in = 0;
 
     for (int b = 0; b < nb; b++) {
         unsigned char *p = smem + (size_t)slot * pl.stage_bytes;
@@ -335,183 +480,128 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
         for (int qq = 0; qq < BW / 4; qq++) {
             const int qi = (DIR == 0) ? BW / 4 - 1 - qq : qq;
             if (c0 + 4 * qi >= W) continue;
-            float xq[K][4], tq[K][4], aq[K][4], gq[5][4];
+            float xq[K][4], aq[K][4], w0q[4], w2q[4], w3q[4];
 #pragma unroll
             for (int i = 0; i < K; i++) {
-                float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vg = vx, va = vx;
-                unsigned mw = 0xffffffffu;
+                float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), va = vx;
                 if (FULL || d0 + i < D) {
                     const unsigned o = tile_swz<BW>((unsigned)(((d0 + i) * BW + 4 * qi) * 4));
                     vx = *reinterpret_cast<const float4 *>(p + pl.off_x + o);
-                    vg = *reinterpret_cast<const float4 *>(p + pl.off_go + o);
                     va = *reinterpret_cast<const float4 *>(p + pl.off_a + o);
-                    mw = *reinterpret_cast<const unsigned *>(p + pl.off_m + (unsigned)((d0 + i) * BW + 4 * qi));
                 }
                 xq[i][0] = vx.x; xq[i][1] = vx.y; xq[i][2] = vx.z; xq[i][3] = vx.w;
                 aq[i][0] = va.x; aq[i][1] = va.y; aq[i][2] = va.z; aq[i][3] = va.w;
-                // get_temp_grad (:38-48): gradOut where this direction won the max
-                tq[i][0] = ((mw & 0xffu) == (unsigned)mask_id) ? vg.x : 0.f;
-                tq[i][1] = (((mw >> 8) & 0xffu) == (unsigned)mask_id) ? vg.y : 0.f;
-                tq[i][2] = (((mw >> 16) & 0xffu) == (unsigned)mask_id) ? vg.z : 0.f;
-                tq[i][3] = ((mw >> 24) == (unsigned)mask_id) ? vg.w : 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const float4 v = *reinterpret_cast<const float4 *>(gt + k * BW + 4 * qi);
-                gq[k][0] = v.x; gq[k][1] = v.y; gq[k][2] = v.z; gq[k][3] = v.w;
+            {
+                const float4 a = *reinterpret_cast<const float4 *>(gt + 0 * BW + 4 * qi);
+                const float4 c = *reinterpret_cast<const float4 *>(gt + 2 * BW + 4 * qi);
+                const float4 d = *reinterpret_cast<const float4 *>(gt + 3 * BW + 4 * qi);
+                w0q[0] = a.x; w0q[1] = a.y; w0q[2] = a.z; w0q[3] = a.w;
+                w2q[0] = c.x; w2q[1] = c.y; w2q[2] = c.z; w2q[3] = c.w;
+                w3q[0] = d.x; w3q[1] = d.y; w3q[2] = d.z; w3q[3] = d.w;
             }
-
-            // ---- phase 0: per step, independent of T -------------------------------------
-            float amax[4], st0[4];
-            int idx[4];
+            float amax[4];
             {
                 float best[4];
-                int bi[4];
 #pragma unroll
                 for (int ss = 0; ss < 4; ss++) {
                     const int e = (DIR == 0) ? 3 - ss : ss;
-                    float bv = (FULL || d0 < D) ? aq[0][e] : -INFINITY;       // strict >: first maximum
-                    int bd = d0;
-                    float t0s = tq[0][e];
+                    float bv = (FULL || d0 < D) ? aq[0][e] : -INFINITY;
 #pragma unroll
-                    for (int i = 1; i < K; i++) {
-                        if ((FULL || d0 + i < D) && aq[i][e] > bv) { bv = aq[i][e]; bd = d0 + i; }
-                        t0s += tq[i][e];
-                    }
-                    best[ss] = bv; bi[ss] = bd; st0[ss] = t0s;
+                    for (int i = 1; i < K; i++)
+                        if (FULL || d0 + i < D) bv = fmaxf(bv, aq[i][e]);
+                    best[ss] = bv;
                 }
 #pragma unroll
                 for (int ss = 0; ss < 4; ss++) amax[ss] = group_max<32>(best[ss]);
-#pragma unroll
-                for (int ss = 0; ss < 4; ss++)
-                    idx[ss] = __reduce_min_sync(kFullMask, best[ss] == amax[ss] ? bi[ss] : 0x7fffffff);
-                const float v = warp_sum4(st0[0], st0[1], st0[2], st0[3], lane);
-#pragma unroll
-                for (int ss = 0; ss < 4; ss++) st0[ss] = __shfl_sync(kFullMask, v, 8 * ss);
             }
 
-            // ---- phase 1: the recurrence (t0 -> T in place in tq) -----------------------------
-            float Tin[K], xin[K], sv[4];
-            const float sum_in = sum_tn;
-            const bool has_in = has_next;
-            const int col_in = col_next;
+            named_barrier(1, 64);                         // the T warp has written this quad
+            float tq[K][4];
 #pragma unroll
-            for (int i = 0; i < K; i++) { Tin[i] = Tn[i]; xin[i] = xn[i]; }
+            for (int i = 0; i < K; i++) {
+                float4 vt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FULL || d0 + i < D)
+                    vt = *reinterpret_cast<const float4 *>(p + pl.off_go + tile_swz<BW>((unsigned)(((d0 + i) * BW + 4 * qi) * 4)));
+                tq[i][0] = vt.x; tq[i][1] = vt.y; tq[i][2] = vt.z; tq[i][3] = vt.w;
+            }
+            const float4 svv = *reinterpret_cast<const float4 *>(svbuf + 4 * quad_parity);
+            const float sv[4] = {svv.x, svv.y, svv.z, svv.w};
+            quad_parity ^= 1;
+
+            // ---- guidance gradients of the four steps (:210-281), then gradInput ----------------
+            float s0[4], s1[4], s2[4], s3[4];
 #pragma unroll
             for (int ss = 0; ss < 4; ss++) {
                 const int e = (DIR == 0) ? 3 - ss : ss;
-                float scur = st0[ss];
-                if (ss > 0 || has_in) {
-                    const float up = __shfl_up_sync(kFullMask, Tn[K - 1], 1);     // T[d0-1, t+1]
-                    const float dn = __shfl_down_sync(kFullMask, Tn[0], 1);       // T[d0+K, t+1]
-                    float tl = Tn[K - 1];
-                    if (!FULL) {
+                const int ep = (DIR == 0) ? e + 1 : e - 1;     // the step processed before (position t+1)
+                s0[ss] = 0.f; s1[ss] = 0.f; s2[ss] = 0.f; s3[ss] = 0.f;
+                const float aup = __shfl_up_sync(kFullMask, aq[K - 1][e], 1);     // A[d0-1, t]
+                const float adn = __shfl_down_sync(kFullMask, aq[0][e], 1);       // A[d0+K, t]
 #pragma unroll
-                        for (int i = 0; i < K; i++)
-                            if (i == i_last) tl = Tn[i];
-                    }
-                    const float t_first = __shfl_sync(kFullMask, Tn[0], 0);       // T[0, t+1]
-                    const float t_last = __shfl_sync(kFullMask, tl, FULL ? 31 : lane_last);   // T[D-1, t+1]
-                    const float inj = sum_tn * wn[4];                             // max-path term (:167-178)
-#pragma unroll
-                    for (int i = 0; i < K; i++) {
-                        const int d = d0 + i;
-                        const float tm = (i == 0) ? up : Tn[i == 0 ? 0 : i - 1];
-                        const float tp = (i == K - 1) ? dn : Tn[i == K - 1 ? K - 1 : i + 1];
-                        float v = tq[i][e];
-                        v += Tn[i] * wn[1];
-                        if (d + 1 < D) v += tp * wn[2];
-                        if (d >= 1) v += tm * wn[3];
-                        if (d == idx[ss]) v += inj;
-                        tq[i][e] = (FULL || d < D) ? v : 0.f;
-                    }
-                    scur += sum_tn * (wn[1] + wn[2] + wn[3] + wn[4]) - wn[2] * t_first - wn[3] * t_last;
+                for (int i = 0; i < K; i++) {
+                    const int d = d0 + i;
+                    const float tp_ = (ss == 0) ? Tin[i] : tq[i][ss == 0 ? e : ep];      // T[d, t+1]
+                    const float xp_ = (ss == 0) ? xin[i] : xq[i][ss == 0 ? e : ep];      // x[d, t+1]
+                    const float am = (i == 0) ? aup : aq[i == 0 ? 0 : i - 1][e];
+                    const float apn = (i == K - 1) ? adn : aq[i == K - 1 ? K - 1 : i + 1][e];
+                    s0[ss] += tq[i][e] * xq[i][e];
+                    s1[ss] += tp_ * aq[i][e];
+                    s2[ss] += tp_ * ((d >= 1) ? am : xp_);
+                    s3[ss] += tp_ * ((d + 1 < D) ? apn : xp_);
                 }
-                sv[ss] = scur;
-                sum_tn = scur;
-#pragma unroll
-                for (int i = 0; i < K; i++) Tn[i] = tq[i][e];
-#pragma unroll
-                for (int k = 0; k < 5; k++) wn[k] = gq[k][e];
             }
-
-            // ---- phase 2: guidance gradients of the four steps, then gradInput ----------------
-            {
-                float s0[4], s1[4], s2[4], s3[4];
+            float tot[4];
 #pragma unroll
-                for (int ss = 0; ss < 4; ss++) {
-                    const int e = (DIR == 0) ? 3 - ss : ss;
-                    const int ep = (DIR == 0) ? e + 1 : e - 1;     // the step processed before (position t+1)
-                    s0[ss] = 0.f; s1[ss] = 0.f; s2[ss] = 0.f; s3[ss] = 0.f;
-                    // A[d0-1, t] and A[d0+K, t]
-                    const float aup = __shfl_up_sync(kFullMask, aq[K - 1][e], 1);
-                    const float adn = __shfl_down_sync(kFullMask, aq[0][e], 1);
+            for (int ss = 0; ss < 4; ss++) tot[ss] = warp_sum4(s0[ss], s1[ss], s2[ss], s3[ss], lane);
 #pragma unroll
-                    for (int i = 0; i < K; i++) {
-                        const int d = d0 + i;
-                        const float tp_ = (ss == 0) ? Tin[i] : tq[i][ss == 0 ? e : ep];      // T[d, t+1]
-                        const float xp_ = (ss == 0) ? xin[i] : xq[i][ss == 0 ? e : ep];      // x[d, t+1]
-                        const float am = (i == 0) ? aup : aq[i == 0 ? 0 : i - 1][e];
-                        const float apn = (i == K - 1) ? adn : aq[i == K - 1 ? K - 1 : i + 1][e];
-                        s0[ss] += tq[i][e] * xq[i][e];
-                        s1[ss] += tp_ * aq[i][e];
-                        s2[ss] += tp_ * ((d >= 1) ? am : xp_);
-                        s3[ss] += tp_ * ((d + 1 < D) ? apn : xp_);
-                    }
+            for (int ss = 0; ss < 4; ss++) {
+                const int e = (DIR == 0) ? 3 - ss : ss;
+                const int col = c0 + 4 * qi + e;
+                const int colp = (ss == 0) ? col_in : ((DIR == 0) ? col + 1 : col - 1);
+                const bool hasp = (ss > 0) || has_in;
+                const float sp = (ss == 0) ? sum_in : sv[ss == 0 ? 0 : ss - 1];
+                // lanes 0 / 8 / 16 / 24 hold the sums s0 (position t) / s1 / s2 / s3 (position t+1)
+                if ((lane & 7) == 0) {
+                    const int k = lane >> 3;
+                    if (k == 0) ggrow[col] = tot[ss];
+                    else if (hasp) ggrow[k * HW + colp] = tot[ss];
                 }
-                float tot[4];
-#pragma unroll
-                for (int ss = 0; ss < 4; ss++) tot[ss] = warp_sum4(s0[ss], s1[ss], s2[ss], s3[ss], lane);
-#pragma unroll
-                for (int ss = 0; ss < 4; ss++) {
-                    const int e = (DIR == 0) ? 3 - ss : ss;
-                    const int col = c0 + 4 * qi + e;
-                    const int colp = (ss == 0) ? col_in : ((DIR == 0) ? col + 1 : col - 1);
-                    const bool hasp = (ss > 0) || has_in;
-                    const float sp = (ss == 0) ? sum_in : sv[ss == 0 ? 0 : ss - 1];
-                    // lanes 0 / 8 / 16 / 24 hold the sums s0 (position t) / s1 / s2 / s3 (position t+1)
-                    if ((lane & 7) == 0) {
-                        const int k = lane >> 3;
-                        if (k == 0) ggrow[col] = tot[ss];
-                        else if (hasp) ggrow[k * HW + colp] = tot[ss];
-                    }
-                    if (lane == 1 && hasp) ggrow[4 * HW + colp] = sp * amax[ss];
-                    if (mirow && lane == 2) mirow[col] = idx[ss];
-                }
-                // gradInput (:164, :177, :200-207), in place over the gradOut tile
-#pragma unroll
-                for (int ss = 0; ss < 4; ss++) {
-                    const int e = (DIR == 0) ? 3 - ss : ss;
-#pragma unroll
-                    for (int i = 0; i < K; i++) {
-                        const int d = d0 + i;
-                        const float t = tq[i][e];
-                        float v = t * gq[0][e];
-                        if (d == 0) v += t * gq[2][e];
-                        if (d == D - 1) v += t * gq[3][e];
-                        tq[i][e] = v;
-                    }
-                }
+                if (lane == 1 && hasp) ggrow[4 * HW + colp] = sp * amax[ss];
             }
             {
                 const int e_last = (DIR == 0) ? 0 : 3;
 #pragma unroll
-                for (int i = 0; i < K; i++) xn[i] = xq[i][e_last];
-                has_next = true;
-                col_next = c0 + 4 * qi + e_last;
+                for (int i = 0; i < K; i++) { Tin[i] = tq[i][e_last]; xin[i] = xq[i][e_last]; }
+                sum_in = sv[3];
+                has_in = true;
+                col_in = c0 + 4 * qi + e_last;
             }
+            // gradInput (:164, :177, :200-207), in place over the T values
 #pragma unroll
-            for (int i = 0; i < K; i++)
-                if (FULL || d0 + i < D)
+            for (int i = 0; i < K; i++) {
+                const int d = d0 + i;
+                if (FULL || d < D) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float t = tq[i][e];
+                        float r = t * w0q[e];
+                        if (d == 0) r += t * w2q[e];
+                        if (d == D - 1) r += t * w3q[e];
+                        v[e] = r;
+                    }
                     *reinterpret_cast<float4 *>(p + pl.off_go + tile_swz<BW>((unsigned)(((d0 + i) * BW + 4 * qi) * 4))) =
-                        make_float4(tq[i][0], tq[i][1], tq[i][2], tq[i][3]);
+                        make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
         }
         fence_proxy_async();
         mbar_arrive(&done[slot]);
         if (++slot == S) { slot = 0; phase ^= 1; }
     }
     // scan position 0 has no predecessor: its guidance gradients 1..4 are zero (A.3 quirk)
-    if (has_next && lane >= 1 && lane <= 4) ggrow[lane * HW + col_next] = 0.f;
+    if (has_in && lane >= 1 && lane <= 4) ggrow[lane * HW + col_in] = 0.f;
 }
 
 // ---------------------------------------------------------------------------
