@@ -682,8 +682,8 @@ static int hscan_prefetch(bool backward)
 {
     static int vf = -1, vb = -1;
     // measured on B200 at the headline size: every distance > 0 is SLOWER (right/left raw 1.46 ->
-    // 1.67 ms at 4 tiles, backward 17.7 -> 18.1 ms): the passes are bound by TMA/L2 requests, not by
-    // DRAM latency, and a prefetch is one more request per row.  Off unless asked for.
+    // 1.67 ms at 4 tiles, backward 17.7 -> 18.1 ms; the vertical kernels likewise): a prefetch is one
+    // more request per row and the memory system is not short of requests.  Off unless asked for.
     if (vf < 0) { const char *e = getenv("GANET_HSCAN_PREFETCH"); vf = e ? atoi(e) : 0; }
     if (vb < 0) { const char *e = getenv("GANET_HSCAN_BWD_PREFETCH"); vb = e ? atoi(e) : 0; }
     return backward ? vb : vf;
@@ -761,21 +761,19 @@ static int launch_hscan_bwd(const float *x, const float *g, const float *a, cons
                             const float *go, float *gi, float *gg, int32_t *max_idx, int mask_id,
                             int accumulate, int D, int H, int W, long long n_slices, cudaStream_t st)
 {
-    constexpr int BW = 32;
+    constexpr int BW = 16;
     const int K = hscan_k(D);
     if (!K || D > 256 || (W % 16) != 0) return kNotApplicable;
     const HBwdPlan pl = hbwd_plan(D, BW);
     const int nb = (W + BW - 1) / BW;
-    // one CTA per SM at the large depths (two 80 KB stages at D = 192), more where the stage is small
-    int S = (kSmemBudget - 4096) / pl.stage_bytes;
+    int S = (kHscanCtaBudget - 2048) / pl.stage_bytes;
     if (S > hscan_stage_cap(true, 4)) S = hscan_stage_cap(true, 4);
-    while (S > 2 && S * pl.stage_bytes > kHscanCtaBudget) S--;
     if (S > nb) S = nb;
     if (S < 2 && nb >= 2) return kNotApplicable;
     if (S < 1) S = 1;
     const size_t smem = (size_t)S * pl.stage_bytes + 2 * S * sizeof(uint64_t) + 64 + 1024;
     HBwdMaps maps;
-    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
     if (!make_plane_map(&maps.x, x, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
     if (!make_plane_map(&maps.go, go, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;
     if (!make_plane_map(&maps.a, a, 4, n_slices * D, H, W, BW, D, 1, sw)) return kNotApplicable;

@@ -224,7 +224,7 @@ __device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, i
 // backward (reverse sweep) of one horizontal direction.  DIR 0 = right (walks the columns
 // DEscending), 1 = left (ascending).  One CTA = one image row; THREE warps:
 //
-//   warp 1  producer: TMA tiles (32 columns, 1 row, D planes) of x, gradOut, A, mask, guidance into a
+//   warp 1  producer: TMA tiles (BW columns, 1 row, D planes) of x, gradOut, A, mask, guidance into a
 //           ring of S stages; stores the gradOut tile, which by then holds gradInput (plain store, or
 //           reduce-add when `accumulate`)
 //   warp 0  "T warp": the sequential part.  Per quad of four scan steps: mask-select gradOut -> T0,
@@ -239,10 +239,11 @@ __device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, i
 //           sum each, written straight to global memory: 80/D bytes per voxel), then
 //           gradInput = T * w0 (+ boundary terms) over the T values in place.
 //
-// Why this shape (profiles/r02_*): a row tile of 64-byte rows moves half the bytes per TMA request
-// of the 128-byte rows and ran request-bound at 3.2 TB/s; 128-byte rows cost 80 KB per stage, i.e.
-// two stages and ONE row per SM, and a single warp per row issues ~250 instructions per step in order --
-// too slow for one SM.  Splitting the step between two warps halves that.
+// Why this shape (profiles/r02_*): a reverse step is ~250 instructions for one warp issuing in order, and
+// shared memory holds few rows per SM (13 bytes per voxel staged: 41 KB per 16-column stage at D = 192).
+// One warp per row, two rows per SM ran at 3.2 TB/s, 45 % of the time waiting for tiles and the rest
+// issue-bound; 32-column tiles (one row per SM) were slower still.  Two warps per row, 16-column
+// tiles, two rows per SM: four working warps per SM.
 // ---------------------------------------------------------------------------
 template <int K, int BW, int DIR, bool FULL>
 __global__ void __launch_bounds__(96)
@@ -250,7 +251,7 @@ sga_hscan_bwd_kernel(const __grid_constant__ HBwdMaps maps, float *__restrict__ 
                      int32_t *__restrict__ max_idx, int mask_id, int accumulate, int D, int H, int W,
                      int S, int PF)
 {
-    static_assert(BW == 32, "128-byte rows");
+    static_assert(BW == 16 || BW == 32, "tile width");
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = align1k(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
