@@ -518,14 +518,18 @@ def run_ours(a):
     sga_gbs = sga_bytes_per_voxel(D) * local_v_sga / t_sga / 1e9 if t_sga > 0 else 0.0
     traffic = load_traffic()
 
-    # launches of OUR kernels in the timed region: SGA fwd 4, SGA bwd 8 per workspace
-    # chunk, LGA2 fwd 2, LGA2 bwd 4 -- per sample per step
-    # launches per native call when the workspace holds the whole call in one chunk:
-    # SGA fwd 9 (3 transposes, 2 horizontal scans, 2 back-transposes, 2 vertical scans) or, keeping
-    # the aggregates, 8 (4 raw scans, 3 transposes, 1 merge); SGA bwd 16, or 11 without the four
-    # recompute scans and T(x); LGA2 fwd 2, LGA2 bwd 4
+    # launches of OUR kernels in the timed region, per native call when the workspace holds the whole
+    # call in one chunk.  Horizontal scans in the standard layout (D <= 256, W % 16 == 0): SGA fwd 5
+    # (four raw scans + merge) / bwd 4 with kept aggregates, fwd 4 / bwd 8 when recomputing.  Transposed
+    # path: fwd 8 / bwd 11 kept, 9 / 16 recomputing.  LGA2 fwd 2, bwd 4.
+    from ganet_b200 import _lib
+    native = _lib.lib().ganet_sga_aggregate_volumes(*[_lib._i64(v) for v in (1, C, D, H, W)]) == 4
+    if native:
+        sga_launches = (5 + 4) if keep_flag[0] else (4 + 8)
+    else:
+        sga_launches = (8 + 11) if keep_flag[0] else (9 + 16)
     calls = a.steps * -(-len(mine) // cs)
-    launches = calls * ((8 + 11 if keep_flag[0] else 9 + 16) + 2 + 4)
+    launches = calls * (sga_launches + 2 + 4)
 
     # ---- roofline of the single hottest kernel family, timed alone ------------------
     # one directional aggregate = ONE launch of the TMA scan kernel in RAW mode: reads x and the
@@ -569,7 +573,7 @@ def run_ours(a):
                        "l2": "inputs larger than L2 (3.7 GB per sample, distinct per sample)",
                        "aggregates_kept_for_backward": bool(keep_flag[0])},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk, "numa": numa,
-            "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (all launches of the call: scans + H<->W transposes + merge)",
+            "roofline": {"bound": "hbm", "kernel": "SGA forward+backward (all launches of the call: four forward scans + merge, four reverse sweeps)",
                          "achieved": sga_gbs, "peak": peak, "unit": "GB/s",
                          "frac": sga_gbs / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": sga_bytes_per_voxel(D),

@@ -35,14 +35,25 @@ class SgaFunction(Function):
     def forward(ctx, input, g0, g1, g2, g3):
         _assert_contiguous(input, g0, g1, g2, g3)
         needs_bwd = any(t.requires_grad for t in (input, g0, g1, g2, g3))
+        agg = None
         if ops.keep_aggregates_policy(input, needs_bwd):
             # memory-for-bandwidth: keep the four directional aggregates (16 B/voxel) so that
-            # backward skips its recompute passes; ops.keep_aggregates_policy decides
-            output, mask, agg = ops.sga_forward(input, g0, g1, g2, g3, keep_aggregates=True)
+            # backward skips its recompute passes; ops.keep_aggregates_policy decides, and an
+            # allocation failure falls back to the recompute variant instead of failing the step
+            try:
+                output, mask, agg = ops.sga_forward(input, g0, g1, g2, g3, keep_aggregates=True)
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                agg = None
+        if agg is not None:
             ctx.save_for_backward(input, g0, g1, g2, g3, mask, agg)
+            nbytes = agg.numel() * 4
+            ops._kept_bytes[0] += nbytes
+            ctx.kept_bytes = nbytes
         else:
             output, mask = ops.sga_forward(input, g0, g1, g2, g3)
             ctx.save_for_backward(input, g0, g1, g2, g3, mask)
+            ctx.kept_bytes = 0
         return output
 
     @staticmethod
@@ -53,6 +64,9 @@ class SgaFunction(Function):
         gradOutput = gradOutput.contiguous()
         gradInput, (grad0, grad1, grad2, grad3) = ops.sga_backward(input, g0, g1, g2, g3, mask,
                                                                    gradOutput, aggregates=agg)
+        if getattr(ctx, "kept_bytes", 0):             # the node's aggregates are about to be released
+            ops._kept_bytes[0] = max(0, ops._kept_bytes[0] - ctx.kept_bytes)
+            ctx.kept_bytes = 0
         return gradInput, grad0, grad1, grad2, grad3
 
 

@@ -27,26 +27,57 @@ def _workspace_budget(device=None):
     return torch.cuda.get_device_properties(device).total_memory // 4
 
 
+def _free_bytes(device):
+    """Bytes a new allocation can count on: free device memory plus what torch's caching
+    allocator holds but has not handed out."""
+    free, _ = torch.cuda.mem_get_info(device)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return int(free + max(0, cached))
+
+
 def _workspace(x, ws_min, ws_best, workspace_bytes):
-    """Scratch for one call: as much of `best` as the budget allows, never below `min`
-    (the native side walks the (n,c) slices in chunks that fit)."""
-    budget = _workspace_budget(x.device) if workspace_bytes is None else int(workspace_bytes)
+    """Scratch for one call: as much of `best` as the budget and the free memory allow, never below
+    `min` (the native side walks the (n,c) slices in chunks that fit).  If even that allocation
+    fails, retry with the minimum before giving up."""
+    if workspace_bytes is None:
+        budget = min(_workspace_budget(x.device), _free_bytes(x.device) // 2)
+    else:
+        budget = int(workspace_bytes)
     nbytes = int(min(ws_best, max(ws_min, budget)))
-    return torch.empty(nbytes, dtype=torch.uint8, device=x.device), nbytes
+    try:
+        return torch.empty(nbytes, dtype=torch.uint8, device=x.device), nbytes
+    except torch.cuda.OutOfMemoryError:
+        if nbytes <= ws_min:
+            raise
+        torch.cuda.empty_cache()
+        return torch.empty(int(ws_min), dtype=torch.uint8, device=x.device), int(ws_min)
+
+
+def aggregate_volumes(x):
+    """How many x-sized fp32 volumes sga_forward(keep_aggregates=True) keeps for this shape (4 when
+    the horizontal scans run in the standard layout, 5 on the transposed path)."""
+    return int(_lib.lib().ganet_sga_aggregate_volumes(*_dims5(x)))
 
 
 def keep_aggregates_policy(x, needs_backward=True):
-    """Should forward keep the four directional aggregates and the transposed input (20 bytes
-    per voxel) so that backward can skip its recompute passes and one transpose?  GANET_B200_KEEP_AGGREGATES = 0 | 1 | auto
-    (default auto: yes when a backward will follow, D <= 288 and three times the buffer is
-    still free on the device -- a 180 GB B200 is there to be used)."""
+    """Should forward keep the directional aggregates (16-20 bytes per voxel) so that backward can skip
+    its recompute passes?  GANET_B200_KEEP_AGGREGATES = 0 | 1 | auto (default auto: yes when a
+    backward will follow, D <= 288 and twice the buffer is available to the allocator -- free
+    device memory plus torch's cached-but-unused blocks).  GANET_B200_KEEP_AGGREGATES_BUDGET caps, in
+    bytes, what all live SgaFunction nodes of the process may hold this way (default: no cap)."""
     mode = os.environ.get("GANET_B200_KEEP_AGGREGATES", "auto")
     if mode == "0" or not needs_backward or x.shape[2] > 288:
         return False
     if mode == "1":
         return True
-    free, _ = torch.cuda.mem_get_info(x.device)
-    return free >= 3 * 20 * x.numel()
+    need = 4 * aggregate_volumes(x) * x.numel()
+    cap = os.environ.get("GANET_B200_KEEP_AGGREGATES_BUDGET")
+    if cap is not None and _kept_bytes[0] + need > int(cap):
+        return False
+    return _free_bytes(x.device) >= 2 * need
+
+
+_kept_bytes = [0]       # bytes of aggregates currently held by autograd nodes (functions.SgaFunction)
 
 
 def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None, keep_aggregates=False):
