@@ -8,6 +8,21 @@ per-sample loss; the all-reduced gradients equal those of the full batch).
 
 The model is the reference's own (baseline/refmodels.py) on the new operators; loss as train.py:116-118
 (SceneFlow branch).  Rank 0 prints one JSON line and exits non-zero if a tolerance is missed.
+
+Two checks in one run:
+
+  frozen   BatchNorm layers use fixed statistics (set once from the whole batch, identically on every
+           rank), so nothing couples the samples: rank r's forward IS the single-GPU forward of sample r.
+           DDP's all-reduced gradient must equal the mean of the per-sample single-GPU gradients to
+           fp32 summation order (1e-4 per tensor) -- this pins the NCCL all-reduce and the operators'
+           behaviour under DDP (unused parameters, autograd hooks).
+  syncbn   nn.SyncBatchNorm in training mode against plain BatchNorm over the whole batch on one GPU.
+           Per-rank losses must equal the single-GPU per-sample losses (1e-4).  The gradients of a
+           freshly initialised GANet are chaotic in the inputs -- a rounding-level change of a
+           BatchNorm statistic flips max / arg-max choices inside SGA and re-routes gradient -- so
+           they are compared by cosine against the same sensitivity measured on ONE GPU (the
+           single-GPU step repeated with the input perturbed by 1e-6): DDP must not be further
+           from the single-GPU gradient than that perturbation is.
 """
 import argparse
 import json
@@ -33,7 +48,6 @@ def main():
     ap.add_argument("--height", type=int, default=240)
     ap.add_argument("--width", type=int, default=624)
     ap.add_argument("--rtol-loss", type=float, default=1e-4)
-    ap.add_argument("--rtol-grad", type=float, default=2e-3)
     a = ap.parse_args()
 
     import torch
@@ -49,61 +63,128 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
 
     gen = torch.Generator(device="cpu").manual_seed(11)
     left = torch.randn(world, 3, a.height, a.width, generator=gen)
     right = torch.randn(world, 3, a.height, a.width, generator=gen)
     target = torch.rand(world, a.height, a.width, generator=gen) * 191.0
 
-    # ---- DDP: rank r owns sample r ---------------------------------------------------
+    def flat_compare(ga, gb):
+        """worst per-tensor max-norm relative error and the cosine of two gradient dicts"""
+        worst, name, dot, na, nb_ = 0.0, None, 0.0, 0.0, 0.0
+        for n, g in ga.items():
+            if n not in gb:                   # a layer the forward never calls: DDP leaves a zero gradient
+                if float(g.abs().max()) != 0.0:
+                    worst, name = float("inf"), n
+                continue
+            ref = gb[n]
+            scale = max(float(ref.abs().max()), 1e-30)
+            err = float((g - ref).abs().max()) / scale
+            if err > worst:
+                worst, name = err, n
+            dot += float((g.double() * ref.double()).sum())
+            na += float((g.double() ** 2).sum()); nb_ += float((ref.double() ** 2).sum())
+        return worst, name, dot / max((na * nb_) ** 0.5, 1e-300)
+
+    def grads_of(module):
+        return {n: p.grad.detach().clone() for n, p in module.named_parameters() if p.grad is not None}
+
+    def bn_layers(module):
+        return [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+
+    def same_everywhere(grads):
+        chk = torch.stack([g.double().sum() for g in grads.values()]).sum()
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(lo == hi)
+
+    l_all, r_all, t_all = left.to(dev), right.to(dev), target.to(dev)
     model = refmodels.build(a.model, 192, seed=5, device=dev)
     state0 = {k: v.clone() for k, v in model.state_dict().items()}
-    ddp = DDP(torch.nn.SyncBatchNorm.convert_sync_batchnorm(model), device_ids=[local])
-    ddp.train()
-    outs = ddp(left[rank:rank + 1].to(dev), right[rank:rank + 1].to(dev))
-    loss = loss_fn(F, outs, target[rank:rank + 1].to(dev))
+    result = {"check": "ddp_step", "model": a.model, "world": world, "height": a.height, "width": a.width}
+    ok = True
+
+    # ---- check 1: frozen BatchNorm statistics --------------------------------------------
+    for m in bn_layers(model):
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(l_all, r_all)                   # every rank: same data, same statistics
+    state_frozen = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def freeze(module):
+        module.train()
+        for m in bn_layers(module):
+            m.eval()
+
+    # the models define a few layers their forward never calls (GANet_deep.py:305 deconv0b): DDP must
+    # be told, or the buckets holding them are never all-reduced
+    ddp = DDP(model, device_ids=[local], find_unused_parameters=True)
+    freeze(ddp)
+    loss = loss_fn(F, ddp(l_all[rank:rank + 1], r_all[rank:rank + 1]), t_all[rank:rank + 1])
     loss.backward()
     losses = [torch.zeros((), device=dev) for _ in range(world)]
     dist.all_gather(losses, loss.detach())
-    grads_ddp = {n: p.grad.detach().clone() for n, p in ddp.module.named_parameters() if p.grad is not None}
-    # every rank must hold the same all-reduced gradient
-    chk = torch.stack([g.double().sum() for g in grads_ddp.values()]).sum()
-    lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    same_on_all_ranks = bool(lo == hi)
-
-    # ---- one GPU, whole batch, plain BatchNorm (statistics over the batch) ------------
-    ok, line = True, None
+    g_ddp = grads_of(ddp.module)
+    same1 = same_everywhere(g_ddp)
     if rank == 0:
         single = refmodels.build(a.model, 192, seed=5, device=dev)
-        single.load_state_dict(state0)
-        single.train()
-        outs1 = single(left.to(dev), right.to(dev))
-        # per-sample losses of the single-GPU run, and the batch loss whose gradient DDP's mean equals
-        per_sample = [loss_fn(F, [o[i:i + 1] for o in outs1], target[i:i + 1].to(dev)) for i in range(world)]
-        total = sum(per_sample) / world
-        total.backward()
-        worst_loss = max(abs(float(losses[i]) - float(per_sample[i])) / abs(float(per_sample[i]))
-                         for i in range(world))
-        worst_grad, worst_name = 0.0, None
-        named = dict(single.named_parameters())
-        for n, g in grads_ddp.items():
-            ref = named[n.replace("module.", "")].grad
-            scale = max(float(ref.abs().max()), 1e-30)
-            err = float((g - ref).abs().max()) / scale
-            if err > worst_grad:
-                worst_grad, worst_name = err, n
-        ok = same_on_all_ranks and worst_loss <= a.rtol_loss and worst_grad <= a.rtol_grad
-        line = {"check": "ddp_step", "model": a.model, "world": world, "height": a.height, "width": a.width,
-                "per_rank_loss": [float(v) for v in losses],
-                "single_gpu_per_sample_loss": [float(v) for v in per_sample],
-                "worst_loss_rel_err": worst_loss, "worst_grad_rel_err": worst_grad,
-                "worst_grad_param": worst_name, "n_param_tensors": len(grads_ddp),
-                "grads_identical_on_all_ranks": same_on_all_ranks,
-                "sync_bn_layers": sum(isinstance(m, torch.nn.SyncBatchNorm) for m in ddp.modules()),
-                "rtol_loss": a.rtol_loss, "rtol_grad": a.rtol_grad, "ok": ok}
-        print(json.dumps(line))
+        single.load_state_dict(state_frozen)
+        freeze(single)
+        per = []
+        for i in range(world):                # one sample at a time: exactly what each rank computed
+            li = loss_fn(F, single(l_all[i:i + 1], r_all[i:i + 1]), t_all[i:i + 1])
+            (li / world).backward()
+            per.append(float(li))
+        worst, name, cos = flat_compare(g_ddp, grads_of(single))
+        wl = max(abs(float(losses[i]) - per[i]) / abs(per[i]) for i in range(world))
+        result["frozen_bn"] = {"per_rank_loss": [float(v) for v in losses], "single_gpu_per_sample_loss": per,
+                               "worst_loss_rel_err": wl, "worst_grad_rel_err": worst, "worst_grad_param": name,
+                               "grad_cosine": cos, "grads_identical_on_all_ranks": same1,
+                               "n_param_tensors": len(g_ddp)}
+        ok = ok and same1 and wl <= a.rtol_loss and worst <= 1e-4 and cos >= 0.999999
+        del single
+    del ddp, g_ddp
+    torch.cuda.empty_cache()
+
+    # ---- check 2: SyncBatchNorm in training mode vs one GPU with the whole batch ------------------
+    model = refmodels.build(a.model, 192, seed=5, device=dev)
+    model.load_state_dict(state0)
+    ddp = DDP(torch.nn.SyncBatchNorm.convert_sync_batchnorm(model), device_ids=[local],
+              find_unused_parameters=True)
+    ddp.train()
+    loss = loss_fn(F, ddp(l_all[rank:rank + 1], r_all[rank:rank + 1]), t_all[rank:rank + 1])
+    loss.backward()
+    dist.all_gather(losses, loss.detach())
+    g_ddp = grads_of(ddp.module)
+    same2 = same_everywhere(g_ddp)
+    n_sync = sum(isinstance(m, torch.nn.SyncBatchNorm) for m in ddp.modules())
+    if rank == 0:
+        def single_step(li_, ri_):
+            single = refmodels.build(a.model, 192, seed=5, device=dev)
+            single.load_state_dict(state0)
+            single.train()
+            outs1 = single(li_, ri_)
+            per_s = [loss_fn(F, [o[i:i + 1] for o in outs1], t_all[i:i + 1]) for i in range(world)]
+            (sum(per_s) / world).backward()
+            return [float(v) for v in per_s], grads_of(single)
+
+        per, g_one = single_step(l_all, r_all)
+        gen2 = torch.Generator(device="cpu").manual_seed(12)
+        noise = 1.0 + 1e-6 * torch.randn(l_all.shape, generator=gen2).to(dev)
+        _, g_pert = single_step(l_all * noise, r_all)
+        worst, name, cos = flat_compare(g_ddp, g_one)
+        _, _, cos_ref = flat_compare(g_pert, g_one)
+        wl = max(abs(float(losses[i]) - per[i]) / abs(per[i]) for i in range(world))
+        result["sync_bn"] = {"per_rank_loss": [float(v) for v in losses], "single_gpu_per_sample_loss": per,
+                             "worst_loss_rel_err": wl, "worst_grad_rel_err": worst, "worst_grad_param": name,
+                             "grad_cosine": cos, "grad_cosine_of_a_1e-6_input_perturbation_on_one_gpu": cos_ref,
+                             "grads_identical_on_all_ranks": same2, "sync_bn_layers": n_sync}
+        ok = ok and same2 and wl <= a.rtol_loss and (1.0 - cos) <= 2.0 * (1.0 - cos_ref) + 1e-6
+        result["ok"] = bool(ok)
+        print(json.dumps(result))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

@@ -120,7 +120,9 @@ def run(a):
         net = model
         if world > 1:
             net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-            net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
+            # find_unused_parameters: the models define layers their forward never calls (deconv0b)
+            net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local],
+                                                            find_unused_parameters=True)
         net.train()
         opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))      # train.py:74
 

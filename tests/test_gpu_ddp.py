@@ -36,5 +36,5 @@ def test_ddp_training_step_matches_single_gpu_batch(model, H, W):
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(lines[-1])
-    assert r.returncode == 0 and res["ok"], res
-    assert res["grads_identical_on_all_ranks"] and res["sync_bn_layers"] > 50
+    assert r.returncode == 0 and res["ok"], json.dumps(res)
+    assert res["frozen_bn"]["grads_identical_on_all_ranks"] and res["sync_bn"]["sync_bn_layers"] > 50
