@@ -142,22 +142,34 @@ lga_tile_kernel(const __grid_constant__ LgaTileMaps maps, const float *__restric
             if (dp < p_hi) {
                 const float *pl = tp + pp * kPlaneFloats;
                 const float ctr = pl[R * kBW + R];
-                float q0[WS], q1[WS], q2[WS];
+                // 75 FMAs per plane as 35 packed fp32 FMAs (fma.rn.f32x2, FFMA2) + 5 scalar ones.  Each
+                // lane of a packed FMA is an ordinary IEEE fma and every accumulator chain keeps its
+                // order (per window row, columns left to right), so the bits are those of lga.cu.
+                //   q01[r] = (depth tap -1 of output dp+1, depth tap 0 of output dp), same input voxel
+                //   q2     = depth tap +1 of output dp-1; rows (0,1) and (2,3) share an instruction
+                float2 q01[WS], q2a, q2b;
+                float q2c = 0.f;
+                q2a = make_float2(0.f, 0.f); q2b = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int r = 0; r < WS; r++) {
-                    q0[r] = 0.f; q1[r] = 0.f; q2[r] = 0.f;
+                for (int r = 0; r < WS; r++) q01[r] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int c = 0; c < WS; c++) {
+                for (int c = 0; c < WS; c++) {
+                    float v[WS];
+#pragma unroll
+                    for (int r = 0; r < WS; r++) v[r] = pl[r * kBW + c];
+#pragma unroll
+                    for (int r = 0; r < WS; r++) {
                         const int t = r * WS + c;
-                        const float v = pl[r * kBW + c];
-                        q0[r] = fmaf(v, wz[0 * P2 + t], q0[r]);    // depth tap -1 of output dp+1
-                        q1[r] = fmaf(v, wz[1 * P2 + t], q1[r]);    // depth tap  0 of output dp
-                        q2[r] = fmaf(v, wz[2 * P2 + t], q2[r]);    // depth tap +1 of output dp-1
+                        q01[r] = __ffma2_rn(make_float2(v[r], v[r]), make_float2(wz[0 * P2 + t], wz[1 * P2 + t]), q01[r]);
                     }
+                    q2a = __ffma2_rn(make_float2(v[0], v[1]), make_float2(wz[2 * P2 + 0 * WS + c], wz[2 * P2 + 1 * WS + c]), q2a);
+                    q2b = __ffma2_rn(make_float2(v[2], v[3]), make_float2(wz[2 * P2 + 2 * WS + c], wz[2 * P2 + 3 * WS + c]), q2b);
+                    q2c = fmaf(v[4], wz[2 * P2 + 4 * WS + c], q2c);
                 }
                 float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 #pragma unroll
-                for (int r = 0; r < WS; r++) { n0 += q0[r]; n1 += q1[r]; n2 += q2[r]; }
+                for (int r = 0; r < WS; r++) { n0 += q01[r].x; n1 += q01[r].y; }
+                n2 += q2a.x; n2 += q2a.y; n2 += q2b.x; n2 += q2b.y; n2 += q2c;
                 a0 += n2; a1 += n1; a2 += n0;
                 // centre-fallback terms of output dp: out-of-image taps always, plus the whole
                 // -1 / +1 depth tap at the volume faces
@@ -241,12 +253,24 @@ lga_tile_filter_kernel(const __grid_constant__ LgaTileMaps maps, const float *__
                 sgc = fmaf(gc, ctr, sgc);
                 if (dp == 0) e_first = gc * ctr;
                 if (dp == D - 1) e_last = gc * ctr;
+                // packed fp32 FMAs: (tap -1, tap 0) of one neighbour share an instruction, the tap +1
+                // accumulators of two neighbours share one; each accumulator still sums over depth in order
+                const float2 gpc = make_float2(gp, gc), gmm = make_float2(gm, gm);
 #pragma unroll
                 for (int t = 0; t < P2; t++) {
                     const float v = pl[(t / WS) * kBW + (t % WS)];
-                    acc[0 * P2 + t] = fmaf(gp, v, acc[0 * P2 + t]);
-                    acc[1 * P2 + t] = fmaf(gc, v, acc[1 * P2 + t]);
-                    acc[2 * P2 + t] = fmaf(gm, v, acc[2 * P2 + t]);
+                    const float2 r = __ffma2_rn(gpc, make_float2(v, v), make_float2(acc[0 * P2 + t], acc[1 * P2 + t]));
+                    acc[0 * P2 + t] = r.x; acc[1 * P2 + t] = r.y;
+                }
+#pragma unroll
+                for (int t = 0; t + 1 < P2; t += 2) {
+                    const float v0 = pl[(t / WS) * kBW + (t % WS)], v1 = pl[((t + 1) / WS) * kBW + ((t + 1) % WS)];
+                    const float2 r = __ffma2_rn(gmm, make_float2(v0, v1), make_float2(acc[2 * P2 + t], acc[2 * P2 + t + 1]));
+                    acc[2 * P2 + t] = r.x; acc[2 * P2 + t + 1] = r.y;
+                }
+                {
+                    const int t = P2 - 1;
+                    acc[2 * P2 + t] = fmaf(gm, pl[(t / WS) * kBW + (t % WS)], acc[2 * P2 + t]);
                 }
                 gm = gc; gc = gp;
             }
