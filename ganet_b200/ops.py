@@ -40,7 +40,9 @@ def _workspace(x, ws_min, ws_best, workspace_bytes):
     `min` (the native side walks the (n,c) slices in chunks that fit).  If even that allocation
     fails, retry with the minimum before giving up."""
     if workspace_bytes is None:
-        budget = min(_workspace_budget(x.device), _free_bytes(x.device) // 2)
+        budget = _workspace_budget(x.device)
+        if ws_best > (1 << 30):          # cudaMemGetInfo costs a driver round trip: only for large requests
+            budget = min(budget, _free_bytes(x.device) // 2)
     else:
         budget = int(workspace_bytes)
     nbytes = int(min(ws_best, max(ws_min, budget)))
@@ -74,6 +76,10 @@ def keep_aggregates_policy(x, needs_backward=True):
     cap = os.environ.get("GANET_B200_KEEP_AGGREGATES_BUDGET")
     if cap is not None and _kept_bytes[0] + need > int(cap):
         return False
+    if need <= (1 << 30):
+        # small calls (the models' shapes: 0.1-1.8 GB of aggregates... up to 1 GB here) skip the driver
+        # query -- it costs more than the call; an allocation failure falls back to recomputing
+        return True
     return _free_bytes(x.device) >= 2 * need
 
 
