@@ -247,3 +247,84 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
     r2 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_reference_arm_is_pinned_fixed_and_flagged():
+    """the CPU arm times a FIXED sample (two full (n,c) slices), with one bound OpenMP thread
+    per physical core, reports the median step and says that ms_per_step is an extrapolation."""
+    import json
+    import subprocess
+    import bench
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert 1 <= bench.physical_cores() <= (os.cpu_count() or 1)
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+           "--warmup", "1", "--depth", "8", "--height", "8", "--width", "16"]
+    env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-1000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["ms_per_step_extrapolated"] is True and d["measured_s_per_step"] > 0
+    assert d["value_min_max"][0] <= d["value"] <= d["value_min_max"][1]          # the median step
+    cb = d["cpu_baseline"]
+    assert cb["omp"] == {"OMP_NUM_THREADS": str(bench.physical_cores()), "OMP_PLACES": "cores",
+                         "OMP_PROC_BIND": "close"}
+    assert "1x2x8x8x16" in cb["sample"] and "1x8x8x16" in cb["sample"]            # fixed shapes, 2 slices
+    # an explicit user setting wins
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(env, OMP_NUM_THREADS="2"))
+    assert json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]["threads"] == 2
+
+
+def test_sync_bn_shim_signature_and_conversion():
+    """libs/sync_bn shim: the reference's constructor arguments (modules/sync_bn.py:64-66) are accepted,
+    state_dict keys are the reference's, and the classes convert to nn.SyncBatchNorm for DDP."""
+    from libs.sync_bn.modules.sync_bn import BatchNorm1d, BatchNorm2d, BatchNorm3d
+    m = BatchNorm2d(4, eps=1e-5, momentum=0.1, sync=False, activation="leaky_relu", slope=0.1, inplace=True)
+    x = torch.randn(2, 4, 3, 3)
+    y = m(x)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(x, None, None, m.weight, m.bias, True, 0.1, 1e-5), 0.1)
+    assert torch.allclose(y, ref, atol=1e-6)
+    assert torch.equal(BatchNorm3d(2)(torch.ones(1, 2, 2, 2, 2)), torch.nn.BatchNorm3d(2)(torch.ones(1, 2, 2, 2, 2)))
+    with pytest.raises(ValueError):
+        BatchNorm1d(3, activation="swish")
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), BatchNorm2d(4), torch.nn.Conv3d(1, 2, 1), BatchNorm3d(2))
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)
+    assert sum(isinstance(k, torch.nn.SyncBatchNorm) for k in conv.modules()) == 2
+    assert sorted(conv[1].state_dict()) == ["bias", "num_batches_tracked", "running_mean", "running_var", "weight"]
+
+
+def test_model_harness_loads_the_copied_reference_models():
+    """baseline/refmodels.py loads models/*.py as copied by oracle/build_ref.py into baseline/_ref/models and
+    wires them to THIS repository's operators; baseline/refops.py finds every hot-path module instance."""
+    from baseline import refmodels
+    if not refmodels.available():
+        pytest.skip("baseline/_ref/models not built (no reference tree at build time)")
+    import ganet_b200.modules as M
+    deep = refmodels.build("GANet_deep", 192, seed=1)
+    assert sum(p.numel() for p in deep.parameters()) == 6580112
+    kinds = [type(m).__name__ for m in deep.modules() if isinstance(m, (M.SGA, M.LGA2, M.GetCostVolume, M.DisparityRegression))]
+    assert kinds.count("SGA") == 7 and kinds.count("GetCostVolume") == 1
+    assert kinds.count("LGA2") == 1 and kinds.count("DisparityRegression") == 3
+    g11 = refmodels.build("GANet11", 192, seed=1)
+    assert sum(isinstance(m, M.SGA) for m in g11.modules()) == 4
+    from baseline.ddp_check import loss_fn
+    import torch.nn.functional as F
+    t = torch.zeros(1, 4, 4)
+    assert float(loss_fn(F, (t + 1, t + 1, t + 1), t)) == pytest.approx(0.2 * 0.5 + 0.6 * 0.5 + 0.5)
+    assert float(loss_fn(F, (t + 1, t + 1), t)) == pytest.approx(0.4 * 0.5 + 1.2 * 0.5)
+
+
+def test_aggregate_volumes_and_workspace_are_consistent(native_so):
+    """The kept-aggregates buffer is 4 volumes where the horizontal scans run in the standard layout (needs the
+    driver's tensor-map encoder, so 5 on a CPU-only box), and then no scratch beyond two aggregates is asked."""
+    from ganet_b200 import _lib
+    L = _lib.lib()
+    i64 = ctypes.c_int64
+    dims = (i64(1), i64(2), i64(24), i64(16), i64(48))
+    S = 24 * 16 * 48
+    v = L.ganet_sga_aggregate_volumes(*dims)
+    assert v in (4, 5)
+    if v == 4:
+        assert L.ganet_sga_forward_workspace_min(*dims) <= 2 * 4 * S + 512
+        assert L.ganet_sga_backward_workspace_min(*dims) <= 4 * S + 256
+    assert L.ganet_sga_aggregate_volumes(i64(1), i64(2), i64(24), i64(16), i64(50)) == 5      # W % 16 != 0
+    assert L.ganet_sga_aggregate_volumes(i64(1), i64(2), i64(288), i64(16), i64(48)) == 5     # D > 256
