@@ -14,7 +14,10 @@ Differences from the reference, all deliberate:
     functions/GANet.py:241; typo `fitlers`, :155), work here with the signature
     the modules call them with;
   * Lgf2Function calls native entry points that never existed upstream
-    (`lgf_cuda_*`, :216); it raises NotImplementedError here.
+    (`lgf_cuda_*`, :216); it raises NotImplementedError here;
+  * MyLoss2Function / MyLossFunction return None as the gradient of the target (input2);
+    upstream returns a one-element CPU zero tensor (`Variable(torch.Tensor([0]))`, :289, :310),
+    which current autograd rejects as soon as the target requires grad -- train.py never asks for it.
 """
 import torch
 from torch.autograd import Function

@@ -42,7 +42,7 @@
  *
  * Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
  * section 8c).  This file is pinned instead against the reference's own
- * kernel bodies compiled for the host (tests/test_oracle_vs_ref.py, bit-exact
+ * kernel bodies compiled for the host (tests/test_oracle.py, bit-exact
  * with fused=0), against vectors generated from them and committed under
  * tests/golden/, and on the GPU box against the unmodified reference CUDA
  * extension (oracle/_ref/GANet*.so, bit-exact with fused=1).
