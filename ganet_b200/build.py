@@ -78,9 +78,49 @@ def build(force=False, verbose=False):
     return SO
 
 
+PYBIND_SRC = os.path.join(CSRC, "ganet_pybind.cpp")
+
+
+def pybind_so():
+    import sysconfig
+    return os.path.join(LIBDIR, "GANet" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind(force=False):
+    """The reference's native module surface as a real pybind11 module named `GANet` over the C ABI
+    (csrc/ganet_pybind.cpp): one host translation unit compiled with g++ against the
+    installed torch, linked to libganet_b200.so next to it ($ORIGIN rpath).  torch is only the tensor
+    plumbing here; the CUDA library itself has no torch dependency."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension
+    build()
+    out = pybind_so()
+    if not force and not _stale(out, [PYBIND_SRC, SO, os.path.join(HERE, "..", "include", "ganet_b200.h")]):
+        return out
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_home = cpp_extension.CUDA_HOME or "/usr/local/cuda"
+    inc = cpp_extension.include_paths() + [sysconfig.get_paths()["include"], os.path.join(cuda_home, "include")]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w",
+           "-DTORCH_EXTENSION_NAME=GANet", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-I" + p for p in inc]
+    cmd += [PYBIND_SRC, "-o", out, "-L" + torch_lib, "-L" + LIBDIR, "-L" + os.path.join(cuda_home, "lib64"),
+            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lganet_b200",
+            "-lcudart", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + torch_lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on ganet_pybind.cpp")
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--pybind", action="store_true", help="also build the pybind11 module `GANet`")
     a = ap.parse_args()
     print(build(a.force, a.verbose))
+    if a.pybind:
+        print(build_pybind(a.force))

@@ -567,10 +567,29 @@ def test_cuda_graph_capture_and_replay(ops):
 
 
 @needs_ref
-def test_legacy_native_surface_matches_reference_extension():
-    """ganet_b200.legacy_native honours the reference's buffer contract
+def _pybind_module():
+    import glob
+    import importlib.util
+    hits = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                         "ganet_b200", "lib", "GANet*.so")))
+    if not hits:
+        pytest.skip("pybind module not built (python -m ganet_b200.build --pybind)")
+    spec = importlib.util.spec_from_file_location("GANet", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@needs_ref
+@pytest.mark.parametrize("surface", ["legacy_native", "pybind"])
+def test_legacy_native_surface_matches_reference_extension(surface):
+    """The reference's native module surface -- as Python adapters (ganet_b200.legacy_native) and as the
+    compiled pybind11 module `GANet` (csrc/ganet_pybind.cpp) -- honours the reference's buffer contract
     (caller-zeroed buffers, accumulate, fp32 mask, temp_out = left aggregate)."""
-    from ganet_b200 import legacy_native as mine
+    if surface == "pybind":
+        mine = _pybind_module()
+    else:
+        from ganet_b200 import legacy_native as mine
     ref = ref_gpu.module()
     shape = (1, 2, 6, 5, 7)
     x, g, go = sga_inputs(shape, seed=15)
@@ -597,6 +616,46 @@ def test_legacy_native_surface_matches_reference_extension():
     mine.lga_cuda_forward(xl, fl, ya, 2)
     ref.lga_cuda_forward(xl, fl, yb, 2)
     assert_close(npy(ya), npy(yb), RTOL, "lga forward")
+
+
+@needs_ref
+def test_reference_python_layer_runs_on_the_pybind_module():
+    """The drop-in test of the NATIVE boundary: the reference's OWN libs/GANet/functions/GANet.py and
+    modules/GANet.py (copied byte for byte to baseline/_ref/reflibs at build time) import
+    `from ..build.lib import GANet` and get this repository's pybind11 module; their SgaFunction and
+    Lga2Function -- the reference's buffer allocation, zero-filling and save_for_backward logic, unmodified --
+    must then give the reference extension's results."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "baseline", "_ref", "reflibs", "GANet", "functions", "GANet.py")):
+        pytest.skip("reference Python layer not copied (oracle/build_ref.py)")
+    _pybind_module()
+    import sys
+    sys.path.insert(0, os.path.join(root, "baseline", "_ref"))
+    try:
+        from reflibs.GANet.modules.GANet import SGA as RefModuleSGA, LGA2 as RefModuleLGA2
+    finally:
+        sys.path.remove(os.path.join(root, "baseline", "_ref"))
+    shape = (1, 2, 24, 16, 48)
+    x, g, go = sga_inputs(shape, seed=23)
+    xt = cu(x).requires_grad_()
+    gt = [cu(a).requires_grad_() for a in g]
+    out = RefModuleSGA()(xt, *gt)                       # reference SgaFunction.forward on our kernels
+    out.backward(cu(go))
+    ro, rm, rtemp = ref_gpu.sga_forward(cu(x), *[cu(a) for a in g])
+    rgi, rgg, _ = ref_gpu.sga_backward(cu(x), *[cu(a) for a in g], rtemp, rm, cu(go))
+    assert torch.equal(out.detach(), ro)
+    assert_close(npy(xt.grad), npy(rgi), RTOL, "gradInput")
+    for d in range(4):
+        assert_close(npy(gt[d].grad), npy(rgg[d]), RTOL, "guidance grad %d" % d)
+    xl, fl, gol = lga_inputs((1, 9, 10, 16), seed=24)
+    xlt, flt = cu(xl).requires_grad_(), cu(fl).requires_grad_()
+    y = RefModuleLGA2(2)(xlt, flt)                      # reference Lga2Function on our kernels
+    y.backward(cu(gol).clone())                         # (the reference's backward overwrites gradOutput)
+    ry, ry1 = ref_gpu.lga2_forward(cu(xl), cu(fl))
+    rgx, rgf = ref_gpu.lga2_backward(cu(xl), cu(fl), ry1, cu(gol).clone())
+    assert_close(npy(y), npy(ry), RTOL, "LGA2 output")
+    assert_close(npy(xlt.grad), npy(rgx), RTOL, "LGA2 grad_x")
+    assert_close(npy(flt.grad), npy(rgf), RTOL, "LGA2 grad_filters")
 
 
 def test_error_reporting(ops):
