@@ -245,6 +245,40 @@ def physical_cores():
     return os.cpu_count() or 1
 
 
+def host_memory_policy(mode):
+    """Placement of the CPU arm's arrays on a multi-socket host.  The reference's kernel bodies run under an
+    OpenMP loop over all cores, but numpy first-touches every array from ONE thread, i.e. on one NUMA node:
+    half the threads then work on remote memory (measured on a 2 x 32-core box: 3.5 s per SGA sample against
+    2.2 s for the same 64 threads confined to one socket).  `interleave` spreads the pages over all nodes
+    (set_mempolicy(MPOL_INTERLEAVE), what `numactl --interleave=all` does); `local` confines the process to
+    node 0's CPUs; `default` leaves the kernel's first-touch policy.  Also undoes an inherited CPU affinity, so
+    that the arm measures the same thing standalone and as bench.py's child."""
+    info = {"policy": mode}
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        nodes = [0]
+    info["nodes"] = len(nodes)
+    if mode == "interleave" and len(nodes) > 1:
+        import ctypes
+        mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+        rc = ctypes.CDLL(None, use_errno=True).syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(64))   # set_mempolicy, MPOL_INTERLEAVE
+        info["set_mempolicy_rc"] = int(rc)
+    elif mode == "local" and len(nodes) > 1:
+        try:
+            with open("/sys/devices/system/node/node%d/cpulist" % nodes[0]) as fh:
+                cpus = _parse_cpulist(fh.read())
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+        except OSError:
+            pass
+    return info
+
+
 def pin_openmp_env():
     """One OpenMP thread per physical core, bound (OMP_PLACES=cores, OMP_PROC_BIND=close): must be in
     the environment before libgomp initialises, i.e. before numpy / the oracle libraries load.
@@ -370,7 +404,7 @@ def run_reference_arm(a):
                                "sample per step)" % (B, C, D, H, W)},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": info["cores"],
                          "threads": info["threads"], "omp": info["omp"], "kind": info["kind"],
-                         "sample": info["sample"]},
+                         "host_memory": getattr(a, "host_memory", None), "sample": info["sample"]},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "config1_cpu": cpu_config1(),
@@ -759,6 +793,7 @@ def main():
         return model_bench.run(a)
     if a.impl == "reference":
         pin_openmp_env()              # before numpy / libgomp load
+        a.host_memory = host_memory_policy(os.environ.get("GANET_CPU_ARM_MEMORY", "interleave"))
         return run_reference_arm(a)
     return run_ours(a)
 
