@@ -249,10 +249,12 @@ def host_memory_policy(mode):
     """Placement of the CPU arm's arrays on a multi-socket host.  The reference's kernel bodies run under an
     OpenMP loop over all cores, but numpy first-touches every array from ONE thread, i.e. on one NUMA node:
     half the threads then work on remote memory (measured on a 2 x 32-core box: 3.5 s per SGA sample against
-    2.2 s for the same 64 threads confined to one socket).  `interleave` spreads the pages over all nodes
-    (set_mempolicy(MPOL_INTERLEAVE), what `numactl --interleave=all` does); `local` confines the process to
-    node 0's CPUs; `default` leaves the kernel's first-touch policy.  Also undoes an inherited CPU affinity, so
-    that the arm measures the same thing standalone and as bench.py's child."""
+    2.2 s for the same 64 threads confined to one socket).  `local` (the default) confines the process to NUMA
+    node 0's CPUs; `interleave` spreads the pages over all nodes (set_mempolicy(MPOL_INTERLEAVE), what
+    `numactl --interleave=all` does); `default` leaves the kernel's first-touch policy.  Measured on the pool's
+    2 x 32-core hosts, whole arm, 64 threads: local 26.4, interleave 16.8, default 16.1 Mvoxel/s (128 threads,
+    interleaved: 13.3) -- so the arm runs the configuration that serves the reference best.  Also undoes an
+    inherited CPU affinity first, so that the arm measures the same thing standalone and as bench.py's child."""
     info = {"policy": mode}
     try:
         os.sched_setaffinity(0, range(os.cpu_count() or 1))
@@ -793,7 +795,7 @@ def main():
         return model_bench.run(a)
     if a.impl == "reference":
         pin_openmp_env()              # before numpy / libgomp load
-        a.host_memory = host_memory_policy(os.environ.get("GANET_CPU_ARM_MEMORY", "interleave"))
+        a.host_memory = host_memory_policy(os.environ.get("GANET_CPU_ARM_MEMORY", "local"))
         return run_reference_arm(a)
     return run_ours(a)
 
