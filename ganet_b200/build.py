@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 SO = os.path.join(LIBDIR, "libganet_b200.so")
-SOURCES = ["sga.cu", "lga.cu", "volume_ops.cu"]
+SOURCES = ["sga.cu", "lga.cu", "volume_ops.cu", "guidance.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -73,6 +73,25 @@ class SgaFunction(Function):
         return gradInput, grad0, grad1, grad2, grad3
 
 
+class SgaGuidanceFunction(Function):
+    """SGABlock prologue, no reference counterpart as a Function: apply(g, channels) returns
+    the four (N, C, 5, H, W) L1-normalised guidance tensors that models/GANet_deep.py:264-268 builds with
+    torch.split + .view + F.normalize(p=1, dim=2) -- one kernel instead of a dozen, bit-identical values --
+    and backward folds the four guidance gradients into the gradient of the raw guidance in one pass."""
+
+    @staticmethod
+    def forward(ctx, g, channels):
+        _assert_contiguous(g)
+        ctx.save_for_backward(g)
+        return ops.sga_guidance_forward(g, channels)
+
+    @staticmethod
+    def backward(ctx, gg0, gg1, gg2, gg3):
+        g, = ctx.saved_tensors
+        return ops.sga_guidance_backward(g, gg0.contiguous(), gg1.contiguous(), gg2.contiguous(),
+                                         gg3.contiguous()), None
+
+
 class _LgaNFunction(Function):
     """`passes` successive LGA passes with shared filters; 4-D or 5-D input."""
     passes = 1

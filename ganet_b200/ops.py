@@ -149,6 +149,31 @@ def sga_backward(x, g0, g1, g2, g3, mask, grad_out, want_max_idx=False, workspac
     return gi, tuple(gg)
 
 
+def sga_guidance_forward(raw, channels):
+    """SGABlock prologue: raw (N, 4*C*5, H, W) guidance -> four L1-normalised (N, C, 5, H, W) weight tensors
+    (down, up, right, left), what models/GANet_deep.py:264-268 computes with split + view + F.normalize."""
+    N, K, H, W = raw.shape
+    C = int(channels)
+    if K != 4 * C * 5:
+        raise ValueError("guidance must have 4*C*5 = %d channels, got %d" % (4 * C * 5, K))
+    with torch.cuda.device_of(raw):
+        g = [torch.empty((N, C, 5, H, W), dtype=raw.dtype, device=raw.device) for _ in range(4)]
+        check(_lib.lib().ganet_sga_guidance_forward(ptr(raw), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]),
+                                                    _i64(N), _i64(C), _i64(H), _i64(W), stream()))
+    return tuple(g)
+
+
+def sga_guidance_backward(raw, gg0, gg1, gg2, gg3):
+    """SGABlock epilogue of backward: gradients w.r.t. the four normalised weight tensors -> gradient of raw."""
+    N, K, H, W = raw.shape
+    C = K // 20
+    with torch.cuda.device_of(raw):
+        out = torch.empty_like(raw)
+        check(_lib.lib().ganet_sga_guidance_backward(ptr(raw), ptr(gg0), ptr(gg1), ptr(gg2), ptr(gg3), ptr(out),
+                                                     _i64(N), _i64(C), _i64(H), _i64(W), stream()))
+    return out
+
+
 def _lga_dims(x, f, radius):
     if x.dim() not in (4, 5):
         raise ValueError("LGA input must be (N,D,H,W) or (N,C,D,H,W)")

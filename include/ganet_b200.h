@@ -165,6 +165,23 @@ int ganet_disp_regression_forward(const float *p, float *disp, int64_t N, int64_
 int ganet_disp_regression_backward(const float *grad_disp, float *grad_p, int64_t N,
                                    int64_t Dm, int64_t H, int64_t W, ganet_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * SGABlock prologue / epilogue.  Replaces, in the reference's MODELS,
+ * models/GANet_deep.py:264-268 (GANet11.py:246-250): torch.split of the guidance conv output into four
+ * (N, C*5, H, W) blocks, .view(N, C, 5, H, W) and F.normalize(p=1, dim=2) of each -- and the autograd
+ * graph of that -- by one streaming pass each way.
+ *   raw    : (N, 4*C*5, H, W), the guidance conv output, direction-major (down, up, right, left)
+ *   g_*    : (N, C, 5, H, W) = raw block / max(sum_j |raw block_j|, 1e-12), bit-identical to F.normalize
+ *   gg_*   : gradients w.r.t. g_* (what ganet_sga_backward returns); grad_raw : (N, 4*C*5, H, W)
+ * H*W must be a multiple of 4.
+ */
+int ganet_sga_guidance_forward(const float *raw, float *g_down, float *g_up, float *g_right,
+                               float *g_left, int64_t N, int64_t C, int64_t H, int64_t W,
+                               ganet_stream_t stream);
+int ganet_sga_guidance_backward(const float *raw, const float *gg_down, const float *gg_up,
+                                const float *gg_right, const float *gg_left, float *grad_raw,
+                                int64_t N, int64_t C, int64_t H, int64_t W, ganet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

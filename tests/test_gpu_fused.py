@@ -1,0 +1,92 @@
+"""the SGABlock prologue fusion, tested against the unfused module path."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _unfused(g, C):
+    """models/GANet_deep.py:264-268 as written."""
+    N, _, H, W = g.shape
+    ks = torch.split(g, (C * 5, C * 5, C * 5, C * 5), 1)
+    return [F.normalize(k.reshape(N, C, 5, H, W), p=1, dim=2) for k in ks]
+
+
+@pytest.mark.parametrize("shape,C", [((1, 640, 80, 208), 32), ((2, 960, 20, 52), 48), ((1, 40, 3, 4), 2)])
+def test_guidance_prologue_matches_f_normalize(shape, C):
+    from ganet_b200.functions import SgaGuidanceFunction
+    torch.manual_seed(7)
+    g = torch.randn(shape, device="cuda")
+    g[0, :5, 0, :2] = 0.0                                        # an all-zero weight vector: the eps clamp
+    g1 = g.clone().requires_grad_()
+    g2 = g.clone().requires_grad_()
+    fused = SgaGuidanceFunction.apply(g1, C)
+    ref = _unfused(g2, C)
+    for a, b in zip(fused, ref):
+        assert a.shape == b.shape and torch.equal(a, b), "normalised guidance differs from F.normalize"
+    go = [torch.randn_like(a) for a in fused]
+    torch.autograd.backward(fused, go)
+    torch.autograd.backward(ref, go)
+    # the zero vector's gradient is g / eps = 1e12 * g on both paths; compare it separately from the rest
+    a, b = g1.grad.clone(), g2.grad.clone()
+    assert_close(a[0, :5, 0, :2].cpu().numpy(), b[0, :5, 0, :2].cpu().numpy(), 1e-5, "clamped entries")
+    a[0, :5, 0, :2] = 0; b[0, :5, 0, :2] = 0
+    assert_close(a.cpu().numpy(), b.cpu().numpy(), 1e-5, "gradient of the raw guidance")
+
+
+def test_fused_sga_blocks_in_the_reference_model():
+    """GANet-11 (reference file, unmodified) with every SGABlock's prologue fused: same disparities bit for
+    bit in eval mode, same loss and gradients in training mode as the unfused model."""
+    from baseline import refmodels
+    from ganet_b200.fused import fuse_sga_blocks, unfuse_sga_blocks
+    if not refmodels.available():
+        pytest.skip("reference models not copied")
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    dev = torch.device("cuda:0")
+    H, W = 96, 192
+    model = refmodels.build("GANet11", 192, seed=3, device=dev).train()
+    gen = torch.Generator(device=dev).manual_seed(4)
+    left = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    right = torch.randn(1, 3, H, W, device=dev, generator=gen)
+    target = torch.rand(1, H, W, device=dev, generator=gen) * 191.0
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        d1, d2 = model(left, right)
+        loss = 0.4 * F.smooth_l1_loss(d1, target) + 1.2 * F.smooth_l1_loss(d2, target)
+        loss.backward()
+        return loss.item(), d2.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    l0, d0, g0 = step()
+    assert fuse_sga_blocks(model) == 4
+    l1, d1, g1 = step()
+    assert unfuse_sga_blocks(model) == 4
+    assert torch.equal(d0, d1), "disparity changed under the fused prologue"
+    assert l0 == l1
+    dot = na = nb = 0.0
+    for n in g0:
+        a, b = g1[n].double(), g0[n].double()
+        dot += float((a * b).sum()); na += float((a * a).sum()); nb += float((b * b).sum())
+    assert dot / (na * nb) ** 0.5 >= 0.99999
+    # launches saved: count our prologue kernel vs torch's normalise chain with the profiler-free proxy of autograd nodes
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    g = torch.randn(1, 640, 80, 208, device=dev, requires_grad=True)
+    from ganet_b200.functions import SgaGuidanceFunction
+    go = [torch.randn(1, 32, 5, 80, 208, device=dev) for _ in range(4)]
+    for fn in (lambda: torch.autograd.backward(_unfused(g, 32), go), lambda: torch.autograd.backward(SgaGuidanceFunction.apply(g, 32), go)):
+        fn()
+    e[0].record()
+    for _ in range(20):
+        torch.autograd.backward(_unfused(g, 32), go)
+    e[1].record()
+    for _ in range(20):
+        torch.autograd.backward(SgaGuidanceFunction.apply(g, 32), go)
+    e[2].record()
+    torch.cuda.synchronize()
+    print("\nSGABlock prologue + its backward at (1,640,80,208): torch split/normalize %.3f ms, fused %.3f ms"
+          % (e[0].elapsed_time(e[1]) / 20, e[1].elapsed_time(e[2]) / 20))
