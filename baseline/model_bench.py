@@ -193,6 +193,16 @@ def run(a):
             dist.all_reduce(flat)
         allreduce_ms = timed(lambda: dist.all_reduce(flat), 10)
 
+    fused = None
+    if getattr(a, "fuse_sga_blocks", False):
+        from ganet_b200.fused import fuse_sga_blocks, unfuse_sga_blocks
+        nblk = fuse_sga_blocks(model)
+        resident()
+        fms = timed(resident, a.steps)
+        unfuse_sga_blocks(model)
+        fused = {"ms": fms if train else fms / nb, "sga_blocks_fused": nblk,
+                 "note": "SGABlock prologue (split + 4x F.normalize) as one kernel each way, SURVEY.md 8f-2"}
+
     ref = None
     if not a.no_ref_gpu and world == 1:
         try:
@@ -228,7 +238,7 @@ def run(a):
                     "api": "model(left, right) from pinned host images; %s read back to the host every step"
                            % ("loss" if train else "disparity map")},
             "hot_path": prof, "gpu_launches": (prof or {}).get("our_launches"), "clocks": clk,
-            "peak_memory_gb": mem_gb, "reference_cuda_on_this_gpu": ref,
+            "peak_memory_gb": mem_gb, "fused_sga_blocks": fused, "reference_cuda_on_this_gpu": ref,
         }
         if train:
             line["nccl"] = {"grad_bytes": n_params * 4, "standalone_allreduce_ms": allreduce_ms,

@@ -153,6 +153,8 @@ def parse_args():
                     help="BASELINE.json config 2/3/4: the reference's models on the new operators "
                          "(baseline/model_bench.py); default: the headline microbenchmark")
     ap.add_argument("--per-gpu-batch", type=int, default=1, help="--config 2-4: samples per GPU")
+    ap.add_argument("--fuse-sga-blocks", action="store_true",
+                    help="--config 2-4: also time the model with the fused SGABlock prologue (ganet_b200.fused)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")

@@ -154,12 +154,12 @@ def main(argv=None):
                 loss, (d0, d1, d2) = train_loss(opt, model(left, right), target, mask, criterion)
                 loss.backward()
                 optimizer.step()
-                errs = [float(torch.mean(torch.abs(d[mask] - target[mask]))) for d in (d0, d1, d2)]
-                sums = [sums[0] + float(loss)] + [s + e for s, e in zip(sums[1:], errs)]
+                errs = [float(torch.mean(torch.abs(d.detach()[mask] - target[mask]))) for d in (d0, d1, d2)]
+                sums = [sums[0] + float(loss.detach())] + [s + e for s, e in zip(sums[1:], errs)]
                 n_ok += 1
                 if rank == 0:
                     print("===> Epoch[{}]({}/{}): Loss: {:.4f}, Error: ({:.4f} {:.4f} {:.4f})".format(
-                        epoch, it, len(loader), float(loss), *errs))
+                        epoch, it, len(loader), float(loss.detach()), *errs))
                     sys.stdout.flush()
             iters += 1
             if opt.max_iters and iters >= opt.max_iters:
