@@ -35,6 +35,8 @@ _SIGNATURES = {
     "ganet_cost_volume_backward": (_int, [_vp] * 3 + [_i64] * 5 + [_vp]),
     "ganet_disp_regression_forward": (_int, [_vp] * 2 + [_i64] * 4 + [_vp]),
     "ganet_disp_regression_backward": (_int, [_vp] * 2 + [_i64] * 4 + [_vp]),
+    "ganet_norm_disp_regression_forward": (_int, [_vp] * 3 + [_i64] * 4 + [_vp]),
+    "ganet_norm_disp_regression_backward": (_int, [_vp] * 5 + [_i64] * 4 + [_vp]),
     "ganet_sga_guidance_forward": (_int, [_vp] * 5 + [_i64] * 4 + [_vp]),
     "ganet_sga_guidance_backward": (_int, [_vp] * 6 + [_i64] * 4 + [_vp]),
 }

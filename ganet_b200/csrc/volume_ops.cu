@@ -96,9 +96,89 @@ disp_regression_bwd_kernel(const float *__restrict__ gdisp, float *__restrict__ 
     for (int d = 0; d < Dm; d++) dst[(long long)d * HW] = g * (float)d;
 }
 
+// DispAgg tail (partial): F.normalize(x, p=1, dim=1) followed by DisparityRegression
+// (models/GANet_deep.py:245-247) in one pass over x:
+//     disp = sum_d d * x_d / max(sum_d |x_d|, 1e-12)
+// The unfused tail reads x, writes the normalised volume, reads it again (and in backward walks the autograd
+// graph of the normalisation); here x is read once each way and nothing of its size is written in forward.
+__global__ void __launch_bounds__(kThreads)
+norm_regression_fwd_kernel(const float *__restrict__ x, float *__restrict__ disp, float *__restrict__ norm,
+                           int Dm, long long HW)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = blockIdx.y;
+    if (i >= HW) return;
+    const float *src = x + n * Dm * HW + i;
+    float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+    int d = 0;
+    for (; d + 1 < Dm; d += 2) {
+        const float v0 = ld_nc(src + (long long)d * HW), v1 = ld_nc(src + (long long)(d + 1) * HW);
+        a0 = fmaf(v0, (float)d, a0); s0 += fabsf(v0);
+        a1 = fmaf(v1, (float)(d + 1), a1); s1 += fabsf(v1);
+    }
+    for (; d < Dm; d++) {
+        const float v0 = ld_nc(src + (long long)d * HW);
+        a0 = fmaf(v0, (float)d, a0); s0 += fabsf(v0);
+    }
+    const float s = fmaxf(s0 + s1, 1e-12f);
+    disp[n * HW + i] = (a0 + a1) / s;
+    norm[n * HW + i] = s0 + s1;                       // unclamped: backward needs to know whether the clamp cut
+}
+
+// gx_d = g * (d - sign(x_d) * disp) / S for S > eps (disp = sum_k k x_k / S), g * d / eps otherwise
+__global__ void __launch_bounds__(kThreads)
+norm_regression_bwd_kernel(const float *__restrict__ x, const float *__restrict__ disp,
+                           const float *__restrict__ norm, const float *__restrict__ gdisp,
+                           float *__restrict__ gx, int Dm, long long HW)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = blockIdx.y;
+    if (i >= HW) return;
+    const float g = ld_nc(gdisp + n * HW + i), dv = ld_nc(disp + n * HW + i), s = ld_nc(norm + n * HW + i);
+    const float *src = x + n * Dm * HW + i;
+    float *dst = gx + n * Dm * HW + i;
+    if (s > 1e-12f) {
+        const float gs = g / s;
+        for (int d = 0; d < Dm; d++) {
+            const float v = ld_nc(src + (long long)d * HW);
+            const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+            dst[(long long)d * HW] = gs * ((float)d - sg * dv);
+        }
+    } else {
+        const float ge = g / 1e-12f;
+        for (int d = 0; d < Dm; d++) dst[(long long)d * HW] = ge * (float)d;
+    }
+}
+
 }  // namespace ganet
 
 using namespace ganet;
+
+GANET_API int ganet_norm_disp_regression_forward(const float *x, float *disp, float *norm, int64_t N,
+                                                 int64_t Dm, int64_t H, int64_t W, ganet_stream_t stream)
+{
+    if (!x || !disp || !norm || N <= 0 || Dm <= 0 || H <= 0 || W <= 0) return GANET_EINVAL;
+    if (N > 65535) return GANET_EUNSUPPORTED;
+    const long long HW = H * W;
+    dim3 grid((unsigned)((HW + kThreads - 1) / kThreads), (unsigned)N);
+    norm_regression_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, disp, norm, (int)Dm, HW);
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
+
+GANET_API int ganet_norm_disp_regression_backward(const float *x, const float *disp, const float *norm,
+                                                  const float *grad_disp, float *grad_x, int64_t N,
+                                                  int64_t Dm, int64_t H, int64_t W, ganet_stream_t stream)
+{
+    if (!x || !disp || !norm || !grad_disp || !grad_x || N <= 0 || Dm <= 0 || H <= 0 || W <= 0) return GANET_EINVAL;
+    if (N > 65535) return GANET_EUNSUPPORTED;
+    const long long HW = H * W;
+    dim3 grid((unsigned)((HW + kThreads - 1) / kThreads), (unsigned)N);
+    norm_regression_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, disp, norm, grad_disp, grad_x,
+                                                                            (int)Dm, HW);
+    GANET_RETURN_IF_LAUNCH_FAILED();
+    return GANET_OK;
+}
 
 GANET_API int ganet_cost_volume_forward(const float *x, const float *y, float *cost, int64_t N,
                                         int64_t C, int64_t Dm, int64_t H, int64_t W,

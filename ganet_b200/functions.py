@@ -238,6 +238,23 @@ class DisparityRegressionFunction(Function):
         return ops.disp_regression_backward(grad_disp.contiguous(), ctx.dm)
 
 
+class NormDispRegressionFunction(Function):
+    """DispAgg tail (partial): F.normalize(x, p=1, dim=1) followed by DisparityRegression
+    (models/GANet_deep.py:245-247) as one pass over x each way."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _assert_contiguous(x)
+        disp, norm = ops.norm_disp_regression_forward(x)
+        ctx.save_for_backward(x, disp, norm)
+        return disp
+
+    @staticmethod
+    def backward(ctx, grad_disp):
+        x, disp, norm = ctx.saved_tensors
+        return ops.norm_disp_regression_backward(x, disp, norm, grad_disp.contiguous())
+
+
 class MyLoss2Function(Function):
     """MyLoss2Function (functions/GANet.py:264-289).  Same piecewise values and
     gradient as upstream, including the order-dependent masked updates (each

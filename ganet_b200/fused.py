@@ -10,7 +10,10 @@ residual) runs as the reference wrote it.  Values are bit-identical to the unfus
 """
 import types
 
-from .functions import SgaGuidanceFunction
+import torch
+import torch.nn.functional as F
+
+from .functions import NormDispRegressionFunction, SgaGuidanceFunction
 
 
 def _fused_sga_block_forward(self, x, g):
@@ -42,6 +45,37 @@ def unfuse_sga_blocks(model):
     n = 0
     for m in model.modules():
         if type(m).__name__ == "SGABlock" and "forward" in m.__dict__:
+            del m.forward
+            n += 1
+    return n
+
+
+def _fused_disp_agg_forward(self, x, lg1, lg2):
+    """DispAgg.forward (models/GANet_deep.py:239-247) with its last two steps -- F.normalize(p=1, dim=1) and the
+    disparity regression -- as one kernel each way (partial)."""
+    x = F.interpolate(self.conv32x1(x), [self.maxdisp + 1, x.size()[3] * 3, x.size()[4] * 3], mode='trilinear',
+                      align_corners=False)
+    x = torch.squeeze(x, 1)
+    assert lg1.size() == lg2.size()
+    x = self.lga(x, lg1)
+    x = self.softmax(x)
+    x = self.lga(x, lg2)
+    return NormDispRegressionFunction.apply(x.contiguous())
+
+
+def fuse_disp_heads(model):
+    n = 0
+    for m in model.modules():
+        if type(m).__name__ == "DispAgg" and hasattr(m, "LGA2") and hasattr(m, "conv32x1"):
+            m.forward = types.MethodType(_fused_disp_agg_forward, m)
+            n += 1
+    return n
+
+
+def unfuse_disp_heads(model):
+    n = 0
+    for m in model.modules():
+        if type(m).__name__ == "DispAgg" and "forward" in m.__dict__:
             del m.forward
             n += 1
     return n

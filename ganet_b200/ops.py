@@ -247,3 +247,23 @@ def disp_regression_backward(grad_disp, Dm):
         check(_lib.lib().ganet_disp_regression_backward(ptr(grad_disp), ptr(gp), _i64(N), _i64(Dm),
                                                         _i64(H), _i64(W), stream()))
     return gp
+
+
+def norm_disp_regression_forward(x):
+    """DispAgg tail: F.normalize(x, p=1, dim=1) + DisparityRegression in one pass -> disp (N,H,W), norm (N,H,W)."""
+    N, Dm, H, W = x.shape
+    with torch.cuda.device_of(x):
+        disp = torch.empty((N, H, W), dtype=x.dtype, device=x.device)
+        norm = torch.empty_like(disp)
+        check(_lib.lib().ganet_norm_disp_regression_forward(ptr(x), ptr(disp), ptr(norm), _i64(N), _i64(Dm),
+                                                            _i64(H), _i64(W), stream()))
+    return disp, norm
+
+
+def norm_disp_regression_backward(x, disp, norm, grad_disp):
+    N, Dm, H, W = x.shape
+    with torch.cuda.device_of(x):
+        gx = torch.empty_like(x)
+        check(_lib.lib().ganet_norm_disp_regression_backward(ptr(x), ptr(disp), ptr(norm), ptr(grad_disp), ptr(gx),
+                                                             _i64(N), _i64(Dm), _i64(H), _i64(W), stream()))
+    return gx

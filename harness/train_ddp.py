@@ -51,7 +51,7 @@ def parse_args(argv=None):
     p.add_argument("--synthetic", type=int, default=0, help="train on this many generated pairs per epoch")
     p.add_argument("--models_dir", type=str, default="", help="directory holding the reference's models/*.py")
     p.add_argument("--max_iters", type=int, default=0, help="stop after this many iterations (smoke runs)")
-    p.add_argument("--fuse_sga_blocks", type=int, default=1, help="fused SGABlock prologue (ganet_b200.fused)")
+    p.add_argument("--fuse_sga_blocks", type=int, default=1, help="fused SGABlock prologue and DispAgg tail (ganet_b200.fused)")
     return p.parse_args(argv)
 
 
@@ -63,8 +63,9 @@ def build_model(opt, device):
         raise Exception("No suitable model found ...")                # train.py:51
     model = refmodels.build(opt.model, opt.max_disp, seed=opt.seed, device=device)
     if opt.fuse_sga_blocks:
-        from ganet_b200.fused import fuse_sga_blocks
+        from ganet_b200.fused import fuse_disp_heads, fuse_sga_blocks
         fuse_sga_blocks(model)
+        fuse_disp_heads(model)
     return model
 
 

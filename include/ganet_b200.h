@@ -165,6 +165,16 @@ int ganet_disp_regression_forward(const float *p, float *disp, int64_t N, int64_
 int ganet_disp_regression_backward(const float *grad_disp, float *grad_p, int64_t N,
                                    int64_t Dm, int64_t H, int64_t W, ganet_stream_t stream);
 
+/* DispAgg tail (partial).  Replaces, in the reference's MODELS, models/GANet_deep.py:245-247:
+ * F.normalize(x, p=1, dim=1) followed by DisparityRegression -- one pass over x each way.
+ *   x : (N, Dm, H, W);  disp : (N, H, W) = sum_d d*x_d / max(sum_d |x_d|, 1e-12);  norm : (N, H, W) scratch
+ *   kept for backward (sum_d |x_d|, unclamped). */
+int ganet_norm_disp_regression_forward(const float *x, float *disp, float *norm, int64_t N, int64_t Dm,
+                                       int64_t H, int64_t W, ganet_stream_t stream);
+int ganet_norm_disp_regression_backward(const float *x, const float *disp, const float *norm,
+                                        const float *grad_disp, float *grad_x, int64_t N, int64_t Dm,
+                                        int64_t H, int64_t W, ganet_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * SGABlock prologue / epilogue.  Replaces, in the reference's MODELS,
  * models/GANet_deep.py:264-268 (GANet11.py:246-250): torch.split of the guidance conv output into four

@@ -90,3 +90,47 @@ def test_fused_sga_blocks_in_the_reference_model():
     torch.cuda.synchronize()
     print("\nSGABlock prologue + its backward at (1,640,80,208): torch split/normalize %.3f ms, fused %.3f ms"
           % (e[0].elapsed_time(e[1]) / 20, e[1].elapsed_time(e[2]) / 20))
+
+
+@pytest.mark.parametrize("shape", [(1, 193, 240, 624), (2, 49, 12, 20), (1, 5, 3, 3)])
+def test_disp_agg_tail_matches_normalize_then_regression(shape):
+    """F.normalize(p=1, dim=1) + DisparityRegression in one pass each way, against the
+    unfused pair (models/GANet_deep.py:245-247) -- no arg-max downstream, so 1e-5 of the disparity range."""
+    from ganet_b200.functions import NormDispRegressionFunction
+    from ganet_b200.modules import DisparityRegression
+    torch.manual_seed(9)
+    x = torch.randn(shape, device="cuda")
+    x[0, :, 0, 0] = 0.0                                          # the eps clamp
+    x1, x2 = x.clone().requires_grad_(), x.clone().requires_grad_()
+    a = NormDispRegressionFunction.apply(x1)
+    b = DisparityRegression(shape[1] - 1)(F.normalize(x2, p=1, dim=1))
+    scale = float(shape[1] - 1)
+    assert float((a - b).abs().max()) <= 1e-5 * scale
+    g = torch.randn_like(a)
+    a.backward(g)
+    b.backward(g)
+    ga, gb = x1.grad.clone(), x2.grad.clone()
+    assert_close(ga[0, :, 0, 0].cpu().numpy(), gb[0, :, 0, 0].cpu().numpy(), 1e-5, "clamped pixel")
+    ga[0, :, 0, 0] = 0; gb[0, :, 0, 0] = 0
+    assert_close(ga.cpu().numpy(), gb.cpu().numpy(), 1e-4, "gradient")
+
+
+def test_fused_disp_head_in_the_reference_model():
+    from baseline import refmodels
+    from ganet_b200.fused import fuse_disp_heads, unfuse_disp_heads
+    if not refmodels.available():
+        pytest.skip("reference models not copied")
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    dev = torch.device("cuda:0")
+    model = refmodels.build("GANet_deep", 192, seed=3, device=dev).train()
+    gen = torch.Generator(device=dev).manual_seed(4)
+    left = torch.randn(1, 3, 96, 192, device=dev, generator=gen)
+    right = torch.randn(1, 3, 96, 192, device=dev, generator=gen)
+    with torch.no_grad():
+        d_ref = model(left, right)[2]
+        assert fuse_disp_heads(model) == 1
+        d_new = model(left, right)[2]
+        assert unfuse_disp_heads(model) == 1
+    err = (d_new - d_ref).abs() / 192.0
+    assert float(err.median()) <= 1e-6 and float((err <= 1e-4).float().mean()) >= 0.99
