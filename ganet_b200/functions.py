@@ -50,13 +50,10 @@ class SgaFunction(Function):
                 agg = None
         if agg is not None:
             ctx.save_for_backward(input, g0, g1, g2, g3, mask, agg)
-            nbytes = agg.numel() * 4
-            ops._kept_bytes[0] += nbytes
-            ctx.kept_bytes = nbytes
+            ops.track_kept_aggregates(agg)           # counted until the buffer is freed, with or without a backward
         else:
             output, mask = ops.sga_forward(input, g0, g1, g2, g3)
             ctx.save_for_backward(input, g0, g1, g2, g3, mask)
-            ctx.kept_bytes = 0
         return output
 
     @staticmethod
@@ -67,9 +64,6 @@ class SgaFunction(Function):
         gradOutput = gradOutput.contiguous()
         gradInput, (grad0, grad1, grad2, grad3) = ops.sga_backward(input, g0, g1, g2, g3, mask,
                                                                    gradOutput, aggregates=agg)
-        if getattr(ctx, "kept_bytes", 0):             # the node's aggregates are about to be released
-            ops._kept_bytes[0] = max(0, ops._kept_bytes[0] - ctx.kept_bytes)
-            ctx.kept_bytes = 0
         return gradInput, grad0, grad1, grad2, grad3
 
 

@@ -86,6 +86,17 @@ def keep_aggregates_policy(x, needs_backward=True):
 _kept_bytes = [0]       # bytes of aggregates currently held by autograd nodes (functions.SgaFunction)
 
 
+def track_kept_aggregates(agg):
+    """Count a kept-aggregates buffer against GANET_B200_KEEP_AGGREGATES_BUDGET for as long as its storage lives."""
+    import weakref
+    nbytes = agg.numel() * agg.element_size()
+    _kept_bytes[0] += nbytes
+
+    def _release(n=nbytes):
+        _kept_bytes[0] = max(0, _kept_bytes[0] - n)
+    weakref.finalize(agg.untyped_storage(), _release)
+
+
 def sga_forward(x, g0, g1, g2, g3, workspace_bytes=None, keep_aggregates=False):
     """-> out (N,C,D,H,W) f32, mask (N,C,D,H,W) u8 [, aggregates (5, N*C*D*H*W) f32]"""
     N, C, D, H, W = x.shape
