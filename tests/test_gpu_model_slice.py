@@ -5,7 +5,7 @@ DispAgg head (:222-247: 3-D conv to one channel, trilinear upsampling, LGA2, sof
 L1 normalisation, DisparityRegression) on a GetCostVolume input -- is run twice from the same
 weights: once on ganet_b200.modules, once on test-only autograd wrappers around the UNMODIFIED
 reference CUDA extension (oracle/_ref/GANet*.so) that restate libs/GANet/functions/GANet.py.
-Outputs and every parameter gradient must agree (fp32, 1e-4 relative; the disparity map and
+Outputs must agree to 1e-4 relative and every parameter gradient to 1e-3 (fp32; the disparity map and
 SGA outputs feed max/argmax paths, so this is also a check that masks agree)."""
 import numpy as np
 import pytest
