@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Inference harness: the reference's predict.py on the B200 operators.
 
-    python harness/predict.py --crop_height 384 --crop_width 1248 --model GANet_deep --resume ckpt.pth \
+    python harness/infer.py --crop_height 384 --crop_width 1248 --model GANet_deep --resume ckpt.pth \
         --left l.png --right r.png --save out.png            # one pair
-    python harness/predict.py ... --kitti2015 1 --data_path D/ --test_list lists/kitti2015_val.list --save_path out/
+    python harness/infer.py ... --kitti2015 1 --data_path D/ --test_list lists/kitti2015_val.list --save_path out/
 
 Pre-processing (per-channel standardisation, padding so the image sits bottom-right, or centre crop) and the
 output format (disparity * 256 as 16-bit PNG, cropped back to the image) follow predict.py:75-138; PIL writes the
@@ -78,7 +78,7 @@ def main(argv=None):
     from PIL import Image
     from harness.train_ddp import build_model, load_checkpoint_into
     if not torch.cuda.is_available():
-        raise SystemExit("harness/predict.py: no CUDA device; the operators have no CPU path")
+        raise SystemExit("harness/infer.py: no CUDA device; the operators have no CPU path")
     dev = torch.device("cuda", 0)
     opt.fuse_sga_blocks = 1
     model = build_model(opt, dev)

@@ -74,7 +74,7 @@ def test_train_resume_predict_round_trip(tmp_path):
     if not refmodels.available():
         pytest.skip("reference models not copied")
     from PIL import Image
-    from harness import predict, train_ddp
+    from harness import infer as predict, train_ddp
     save = str(tmp_path / "ck")
     args = ["--crop_height", "48", "--crop_width", "96", "--max_disp", "48", "--model", "GANet11", "--synthetic", "4",
             "--batchSize", "1", "--nEpochs", "1", "--max_iters", "2", "--threads", "0", "--save_path", save]
