@@ -330,3 +330,19 @@ def test_aggregate_volumes_and_workspace_are_consistent(native_so):
         assert L.ganet_sga_backward_workspace_min(*dims) <= 4 * S + 256
     assert L.ganet_sga_aggregate_volumes(i64(1), i64(2), i64(24), i64(16), i64(50)) == 5      # W % 16 != 0
     assert L.ganet_sga_aggregate_volumes(i64(1), i64(2), i64(288), i64(16), i64(48)) == 5     # D > 256
+
+
+def test_model_patchers_find_the_reference_blocks():
+    """ganet_b200.fused patches the reference's SGABlock / DispAgg instances by class name (models/*.py stay
+    untouched) and undoes it; counts are the models' (GANet_deep.py:305-315: 7 SGABlocks, one DispAgg)."""
+    from baseline import refmodels
+    if not refmodels.available():
+        pytest.skip("baseline/_ref/models not built")
+    from ganet_b200 import fused
+    deep = refmodels.build("GANet_deep", 192, seed=1)
+    assert fused.fuse_sga_blocks(deep) == 7 and fused.fuse_disp_heads(deep) == 1
+    blk = deep.cost_agg.sga1
+    assert "forward" in blk.__dict__ and blk.forward.__func__ is fused._fused_sga_block_forward
+    assert fused.unfuse_sga_blocks(deep) == 7 and fused.unfuse_disp_heads(deep) == 1
+    assert "forward" not in blk.__dict__ and type(blk).forward is not fused._fused_sga_block_forward
+    assert fused.fuse_sga_blocks(refmodels.build("GANet11", 192, seed=1)) == 4
